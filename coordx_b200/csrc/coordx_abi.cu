@@ -1,0 +1,406 @@
+// C ABI of coordx_b200 (see include/coordx_b200.h).  Host-side orchestration of the
+// CUDA kernels; no torch types, no allocation, no synchronisation.
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_f32.cuh"
+#include "trunk_tc.cuh"
+
+namespace coordx {
+
+thread_local char g_err[512] = "";
+
+struct Layer {
+  const float* W;
+  const float* b;
+  float bscale;
+  int in, out;
+  int act;          // COORDX_ACT_* or -1 (identity)
+  float* dW;
+  float* db;
+};
+
+// Y_l = act_l(X_l W_l^T + b_l * bscale_l), chained.  If Zs/As are given, every layer's
+// pre-activation / output is kept (As[nl-1] == Yfinal unless Yfinal is null).
+static int mlp_forward(const Layer* L, int nl, const float* X, int64_t ldx, int M, float* Yfinal, float* const* Zs,
+                       float* const* As, float* tmp0, float* tmp1, float S, cudaStream_t st) {
+  const float* cur = X;
+  int64_t ld = ldx;
+  for (int l = 0; l < nl; ++l) {
+    float* y = (l == nl - 1 && Yfinal) ? Yfinal : (As ? As[l] : ((l & 1) ? tmp1 : tmp0));
+    float* z = Zs ? Zs[l] : nullptr;
+    CX_TRY(linear_forward(cur, ld, L[l].W, L[l].b, L[l].bscale, M, L[l].out, L[l].in, y, z, L[l].out, L[l].act, S, st));
+    cur = y;
+    ld = L[l].out;
+  }
+  return 0;
+}
+
+// Backward of mlp_forward.  dY = gradient w.r.t. the chain output.  d0/d1: scratch of
+// M * max width floats.  dX (nullable) [M, L[0].in].
+static int mlp_backward(const Layer* L, int nl, const float* X, int64_t ldx, int M, float* const* Zs, float* const* As,
+                        const float* dY, float* d0, float* d1, float* dX, float S, cudaStream_t st) {
+  const float* dz = dY;
+  float* bufs[2] = {d0, d1};
+  int which = 0;
+  if (L[nl - 1].act >= 0) {
+    const int64_t cnt = (int64_t)M * L[nl - 1].out;
+    mul_act_grad_kernel<<<(unsigned)cdiv(cnt, 256), 256, 0, st>>>(dY, Zs[nl - 1], bufs[which], cnt, L[nl - 1].act, S);
+    CX_LAUNCH_CHECK();
+    dz = bufs[which];
+    which ^= 1;
+  }
+  for (int l = nl - 1; l >= 0; --l) {
+    const float* in = l == 0 ? X : As[l - 1];
+    const int64_t ldin = l == 0 ? ldx : L[l - 1].out;
+    if (L[l].dW) CX_TRY(linear_backward_dw(dz, L[l].out, in, ldin, M, L[l].out, L[l].in, L[l].dW, st));
+    if (L[l].db) CX_TRY(bias_backward(dz, L[l].out, M, L[l].out, L[l].bscale, L[l].db, st));
+    if (l > 0) {
+      const bool has_act = L[l - 1].act >= 0;
+      CX_TRY(linear_backward_dx(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, bufs[which], L[l].in,
+                                has_act ? Zs[l - 1] : nullptr, L[l - 1].out, L[l - 1].act, S, st));
+      dz = bufs[which];
+      which ^= 1;
+    } else if (dX) {
+      CX_TRY(linear_backward_dx(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, dX, L[l].in, nullptr, 0, -1, S, st));
+    }
+  }
+  return 0;
+}
+
+static int check_net(const coordx_net* net) {
+  if (!net) return set_err(COORDX_ERR_ARG, "net is null%s");
+  if (net->n_branches < 1 || net->n_branches > COORDX_MAX_BRANCHES) return set_err(COORDX_ERR_ARG, "n_branches out of range%s (%lld)", "", net->n_branches);
+  if (net->n_layers < 1 || net->n_layers > COORDX_MAX_LAYERS || net->n_pre < 0 || net->n_pre > net->n_layers)
+    return set_err(COORDX_ERR_ARG, "bad layer counts%s (n_pre %lld, n_layers %lld)", "", net->n_pre, net->n_layers);
+  if (net->fusion_op != COORDX_FUSE_SUM && net->fusion_op != COORDX_FUSE_PROD)
+    return set_err(COORDX_ERR_ARG, "unknown fusion operator%s (%lld)", "", net->fusion_op);   // the reference silently skips the fusion (modules.py:336-341)
+  if (net->act != COORDX_ACT_SINE && net->act != COORDX_ACT_RELU) return set_err(COORDX_ERR_ARG, "unknown activation%s (%lld)", "", net->act);
+  if (net->hidden <= 0 || net->fuse_width % net->hidden != 0) return set_err(COORDX_ERR_ARG, "fuse_width must be a multiple of hidden%s");
+  return 0;
+}
+
+// layers of branch `b`: coord_linears[b] then net[0..n_pre-1]
+static int branch_layers(const coordx_net* net, int b, const coordx_grads* g, Layer* L) {
+  int nl = 0;
+  L[nl++] = Layer{net->first_w[b], net->first_b[b], 1.f, net->branch_in[b], net->pre_width, net->act,
+                  g ? g->first_w[b] : nullptr, g ? g->first_b[b] : nullptr};
+  for (int k = 0; k < net->n_pre; ++k) {
+    const bool last = (k == net->n_pre - 1);
+    const bool noact = last && (net->fusion_before_act || k == net->n_layers - 1);
+    L[nl++] = Layer{net->layer_w[k], net->layer_b[k], 1.f / net->n_branches, net->layer_in[k], net->layer_out[k],
+                    noact ? -1 : net->act, g ? g->layer_w[k] : nullptr, g ? g->layer_b[k] : nullptr};
+  }
+  return nl;
+}
+
+static int trunk_layers(const coordx_net* net, const coordx_grads* g, Layer* L) {
+  int nl = 0;
+  for (int k = net->n_pre; k < net->n_layers; ++k)
+    L[nl++] = Layer{net->layer_w[k], net->layer_b[k], 1.f, net->layer_in[k], net->layer_out[k],
+                    k == net->n_layers - 1 ? -1 : net->act, g ? g->layer_w[k] : nullptr, g ? g->layer_b[k] : nullptr};
+  return nl;
+}
+
+struct ChainWs {
+  float* Z[COORDX_MAX_LAYERS + 1];
+  float* A[COORDX_MAX_LAYERS + 1];
+  float* d0;
+  float* d1;
+  float* tmp0;
+  float* tmp1;
+};
+
+static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backward, ChainWs& w) {
+  int maxw = 1;
+  for (int l = 0; l < nl; ++l) maxw = max(maxw, max(L[l].in, L[l].out));
+  if (backward) {
+    for (int l = 0; l < nl; ++l) {
+      w.Z[l] = ar.get<float>((size_t)M * L[l].out);
+      w.A[l] = ar.get<float>((size_t)M * L[l].out);
+    }
+    w.d0 = ar.get<float>((size_t)M * maxw);
+    w.d1 = ar.get<float>((size_t)M * maxw);
+    w.tmp0 = w.tmp1 = nullptr;
+  } else {
+    w.tmp0 = ar.get<float>((size_t)M * maxw);
+    w.tmp1 = ar.get<float>((size_t)M * maxw);
+  }
+}
+
+// ------------------------------------------------------------------ trunk planning (fp32 path)
+struct TrunkPlan {
+  int64_t inner;        // prod_{c>0} n_c
+  int64_t chunk_rows;   // whole axis-0 rows per chunk
+  int64_t chunk_pts;
+};
+
+static TrunkPlan plan_trunk(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1) {
+  TrunkPlan pl{};
+  pl.inner = 1;
+  for (int c = 1; c < net->n_branches; ++c) pl.inner *= n[c];
+  const int64_t target = 32768;      // points per chunk: [chunk, 256] fp32 = 32 MB, stays L2-resident
+  pl.chunk_rows = max((int64_t)1, min(r1 - r0, target / max(pl.inner, (int64_t)1)));
+  pl.chunk_pts = pl.chunk_rows * pl.inner;
+  return pl;
+}
+
+static FuseArgs make_fuse_args(const coordx_net* net, const float* const* feats, const int64_t* n, const TrunkPlan& pl) {
+  FuseArgs a{};
+  a.C = net->n_branches;
+  for (int c = 0; c < a.C; ++c) { a.feat[c] = feats[c]; a.n[c] = n[c]; }
+  a.F = net->fuse_width;
+  a.Hd = net->hidden;
+  a.gs = net->fuse_width / net->hidden;
+  a.op = net->fusion_op;
+  a.fba = net->fusion_before_act;
+  a.act = net->act;
+  a.S = 30.f * net->act_scale;
+  a.code = net->has_code ? net->code : nullptr;
+  a.inner = pl.inner;
+  return a;
+}
+
+}  // namespace coordx
+
+using namespace coordx;
+
+extern "C" {
+
+int coordx_abi_version(void) { return COORDX_ABI_VERSION; }
+const char* coordx_last_error(void) { return g_err; }
+
+int coordx_trunk_tc_supported(const coordx_net* net, int precision) {
+  if (check_net(net) != 0) return 0;
+  return tc::tc_supported(net, precision) ? 1 : 0;
+}
+
+// -------------------------------------------------------------------------- branch
+size_t coordx_branch_workspace_bytes(const coordx_net* net, int branch, int64_t n, int backward) {
+  if (check_net(net) != 0 || branch < 0 || branch >= net->n_branches) return 0;
+  Layer L[COORDX_MAX_LAYERS + 1];
+  const int nl = branch_layers(net, branch, nullptr, L);
+  Arena ar(nullptr, 0);
+  ChainWs w{};
+  carve_chain(ar, L, nl, n, backward != 0, w);
+  return ar.off + 256;
+}
+
+int coordx_branch_forward(const coordx_net* net, int branch, const float* coords, int64_t n, float* feat, void* ws,
+                          size_t ws_bytes, void* stream) {
+  CX_TRY(check_net(net));
+  if (branch < 0 || branch >= net->n_branches) return set_err(COORDX_ERR_ARG, "branch out of range%s (%lld)", "", branch);
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layer L[COORDX_MAX_LAYERS + 1];
+  const int nl = branch_layers(net, branch, nullptr, L);
+  Arena ar(ws, ws_bytes);
+  ChainWs w{};
+  carve_chain(ar, L, nl, n, false, w);
+  if (!ar.ok() || (nl > 1 && !w.tmp0)) return set_err(COORDX_ERR_WORKSPACE, "branch forward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
+  return mlp_forward(L, nl, coords, net->branch_in[branch], (int)n, feat, nullptr, nullptr, w.tmp0, w.tmp1,
+                     30.f * net->act_scale, st);
+}
+
+int coordx_branch_backward(const coordx_net* net, int branch, const float* coords, int64_t n, const float* dfeat,
+                           coordx_grads* grads, float* dcoords, void* ws, size_t ws_bytes, void* stream) {
+  CX_TRY(check_net(net));
+  if (branch < 0 || branch >= net->n_branches) return set_err(COORDX_ERR_ARG, "branch out of range%s (%lld)", "", branch);
+  if (!grads) return set_err(COORDX_ERR_ARG, "grads is null%s");
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layer L[COORDX_MAX_LAYERS + 1];
+  const int nl = branch_layers(net, branch, grads, L);
+  Arena ar(ws, ws_bytes);
+  ChainWs w{};
+  carve_chain(ar, L, nl, n, true, w);
+  if (!ar.ok() || !ws) return set_err(COORDX_ERR_WORKSPACE, "branch backward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
+  const float S = 30.f * net->act_scale;
+  CX_TRY(mlp_forward(L, nl, coords, net->branch_in[branch], (int)n, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
+  return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords, S, st);
+}
+
+// -------------------------------------------------------------------------- trunk
+size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t row_begin, int64_t row_end,
+                                    int precision, int backward) {
+  if (check_net(net) != 0 || !n) return 0;
+  if (precision != COORDX_PREC_FP32 && !backward) {
+    if (!tc::tc_supported(net, precision)) return 0;
+    return tc::plan_fwd(n[net->n_branches - 1]).total + 1024;
+  }
+  const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
+  Layer L[COORDX_MAX_LAYERS + 1];
+  const int nl = trunk_layers(net, nullptr, L);
+  Arena ar(nullptr, 0);
+  ar.get<float>((size_t)pl.chunk_pts * net->hidden);     // H0
+  if (backward) ar.get<float>((size_t)pl.chunk_pts * net->hidden);   // dH0
+  ChainWs w{};
+  if (nl > 0) carve_chain(ar, L, nl, pl.chunk_pts, backward != 0, w);
+  return ar.off + 256;
+}
+
+int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
+                         int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, void* stream) {
+  CX_TRY(check_net(net));
+  if (!feats || !n || !out) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (row_begin < 0 || row_end > n[0] || row_begin > row_end) return set_err(COORDX_ERR_ARG, "bad slab%s [%lld, %lld)", "", row_begin, row_end);
+  if (row_begin == row_end) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision != COORDX_PREC_FP32) {
+    if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
+    return tc::trunk_forward_tc(net, feats, n, row_begin, row_end, out, precision, ws, ws_bytes, st);
+  }
+  const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
+  Layer L[COORDX_MAX_LAYERS + 1];
+  const int nl = trunk_layers(net, nullptr, L);
+  Arena ar(ws, ws_bytes);
+  float* H0 = ar.get<float>((size_t)pl.chunk_pts * net->hidden);
+  ChainWs w{};
+  if (nl > 0) carve_chain(ar, L, nl, pl.chunk_pts, false, w);
+  if (!ws || !ar.ok()) return set_err(COORDX_ERR_WORKSPACE, "trunk forward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
+  FuseArgs fa = make_fuse_args(net, feats, n, pl);
+  const float S = 30.f * net->act_scale;
+  const int ow = nl > 0 ? L[nl - 1].out : net->hidden;
+  for (int64_t r = row_begin; r < row_end; r += pl.chunk_rows) {
+    const int64_t rows = min(pl.chunk_rows, row_end - r);
+    const int64_t pts = rows * pl.inner;
+    fa.row0 = r;
+    fa.nrows = rows;
+    float* o = out + (r - row_begin) * pl.inner * ow;
+    float* h0 = nl > 0 ? H0 : o;            // approx_layers == num_hidden_layers+1: the fused value is the output
+    fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, h0);
+    CX_LAUNCH_CHECK();
+    if (nl > 0) CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, o, nullptr, nullptr, w.tmp0, w.tmp1, S, st));
+  }
+  return 0;
+}
+
+int coordx_trunk_backward(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
+                          int64_t row_end, const float* dout, coordx_grads* grads, float* const* dfeat, int precision,
+                          void* ws, size_t ws_bytes, void* stream) {
+  CX_TRY(check_net(net));
+  if (!feats || !n || !dout || !grads || !dfeat) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (row_begin < 0 || row_end > n[0] || row_begin > row_end) return set_err(COORDX_ERR_ARG, "bad slab%s [%lld, %lld)", "", row_begin, row_end);
+  if (row_begin == row_end) return 0;
+  (void)precision;   // round 1: the backward always runs the FP32 kernels
+  cudaStream_t st = (cudaStream_t)stream;
+  const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
+  Layer L[COORDX_MAX_LAYERS + 1];
+  const int nl = trunk_layers(net, grads, L);
+  Arena ar(ws, ws_bytes);
+  float* H0 = ar.get<float>((size_t)pl.chunk_pts * net->hidden);
+  float* dH0 = ar.get<float>((size_t)pl.chunk_pts * net->hidden);
+  ChainWs w{};
+  if (nl > 0) carve_chain(ar, L, nl, pl.chunk_pts, true, w);
+  if (!ws || !ar.ok()) return set_err(COORDX_ERR_WORKSPACE, "trunk backward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
+  FuseArgs fa = make_fuse_args(net, feats, n, pl);
+  const float S = 30.f * net->act_scale;
+  const int ow = nl > 0 ? L[nl - 1].out : net->hidden;
+  const int C = net->n_branches;
+  for (int64_t r = row_begin; r < row_end; r += pl.chunk_rows) {
+    const int64_t rows = min(pl.chunk_rows, row_end - r);
+    const int64_t pts = rows * pl.inner;
+    fa.row0 = r;
+    fa.nrows = rows;
+    const float* dY = dout + (r - row_begin) * pl.inner * ow;
+    const float* dh = dY;
+    if (nl > 0) {
+      fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, H0);
+      CX_LAUNCH_CHECK();
+      CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
+      CX_TRY(mlp_backward(L, nl, H0, net->hidden, (int)pts, w.Z, w.A, dY, w.d0, w.d1, dH0, S, st));
+      dh = dH0;
+    }
+    for (int b = 0; b < C; ++b) {
+      const int64_t cnt_b = b == 0 ? rows : n[b];
+      const int64_t T = pts / cnt_b;
+      // spread the reduction over the chip: ~4 waves of 128-thread blocks
+      const int64_t base_blocks = cdiv(net->fuse_width, 128) * cnt_b;
+      int64_t splits = max((int64_t)1, min(cdiv(T, 64), cdiv((int64_t)148 * 16, base_blocks)));
+      const int64_t tpb = cdiv(T, splits);
+      splits = cdiv(T, tpb);
+      dim3 grid((unsigned)cnt_b, (unsigned)cdiv(net->fuse_width, 128), (unsigned)splits);
+      if (splits > 65535) return set_err(COORDX_ERR_UNSUPPORTED, "axis too long for fuse_bwd grid%s (%lld)", "", cnt_b);
+      fuse_bwd_kernel<<<grid, 128, 0, st>>>(fa, b, dh, dfeat[b], (b == 0 && net->has_code) ? grads->code : nullptr, T, tpb);
+      CX_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------- loss / optimiser
+int coordx_loss_forward_backward(int kind, const float* out, const float* gt, int64_t numel, float inv_count,
+                                 float* loss_accum, float* dout, void* stream) {
+  if (kind != COORDX_LOSS_MSE && kind != COORDX_LOSS_BCE) return set_err(COORDX_ERR_ARG, "unknown loss%s (%lld)", "", kind);
+  if (!out || !gt || !loss_accum) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (numel <= 0) return 0;
+  const int blocks = (int)min((int64_t)148 * 8, cdiv(numel, 256));
+  loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kind, out, gt, numel, inv_count, loss_accum, dout);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+int coordx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                     float beta1, float beta2, float eps, int64_t step_host, const float* grad_scale_dev, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step_host < 1) return set_err(COORDX_ERR_ARG, "bad adam argument%s");
+  if (numel <= 0) return 0;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step_host);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step_host);
+  adam_kernel<<<(unsigned)cdiv(numel, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, numel, (float)(lr / bc1),
+                                                                          beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), grad_scale_dev);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+// -------------------------------------------------------------------------- host-buffer inference
+size_t coordx_infer_grid_host_workspace_bytes(const coordx_net* net, const int64_t* n, int precision) {
+  if (check_net(net) != 0 || !n) return 0;
+  size_t total = 0;
+  int64_t P = 1;
+  for (int c = 0; c < net->n_branches; ++c) {
+    P *= n[c];
+    total += align_up((size_t)n[c] * net->branch_in[c] * 4, 256);       // coords
+    total += align_up((size_t)n[c] * net->fuse_width * 4, 256);         // features
+  }
+  size_t bws = 0;
+  for (int c = 0; c < net->n_branches; ++c) bws = max(bws, coordx_branch_workspace_bytes(net, c, n[c], 0));
+  const size_t tws = coordx_trunk_workspace_bytes(net, n, 0, n[0], precision, 0);
+  total += align_up(max(bws, tws), 256);
+  total += align_up((size_t)P * net->layer_out[net->n_layers - 1] * 4, 256);   // out
+  return total + 1024;
+}
+
+int coordx_infer_grid_host(const coordx_net* net, const float* const* coords_host, const int64_t* n, float* out_host,
+                           int precision, void* ws, size_t ws_bytes, void* stream) {
+  CX_TRY(check_net(net));
+  if (!coords_host || !n || !out_host || !ws) return set_err(COORDX_ERR_ARG, "null argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = net->n_branches;
+  Arena ar(ws, ws_bytes);
+  float* dcoords[COORDX_MAX_BRANCHES];
+  float* dfeat[COORDX_MAX_BRANCHES];
+  int64_t P = 1;
+  for (int c = 0; c < C; ++c) {
+    P *= n[c];
+    dcoords[c] = ar.get<float>((size_t)n[c] * net->branch_in[c]);
+    dfeat[c] = ar.get<float>((size_t)n[c] * net->fuse_width);
+  }
+  size_t bws = 0;
+  for (int c = 0; c < C; ++c) bws = max(bws, coordx_branch_workspace_bytes(net, c, n[c], 0));
+  const size_t tws = coordx_trunk_workspace_bytes(net, n, 0, n[0], precision, 0);
+  const size_t sws = max(bws, tws);
+  char* scratch = ar.get<char>(sws);
+  const int ow = net->layer_out[net->n_layers - 1];
+  float* dout = ar.get<float>((size_t)P * ow);
+  if (!ar.ok() || !dout) return set_err(COORDX_ERR_WORKSPACE, "infer_grid_host: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
+  for (int c = 0; c < C; ++c) {
+    CX_CUDA(cudaMemcpyAsync(dcoords[c], coords_host[c], (size_t)n[c] * net->branch_in[c] * 4, cudaMemcpyHostToDevice, st));
+    CX_TRY(coordx_branch_forward(net, c, dcoords[c], n[c], dfeat[c], scratch, sws, stream));
+  }
+  const float* feats[COORDX_MAX_BRANCHES];
+  for (int c = 0; c < C; ++c) feats[c] = dfeat[c];
+  CX_TRY(coordx_trunk_forward(net, feats, n, 0, n[0], dout, precision, scratch, sws, stream));
+  CX_CUDA(cudaMemcpyAsync(out_host, dout, (size_t)P * ow * 4, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// FP32 (FFMA) GEMM family for the 1e-5-relative parity path and for every
+// configuration the tcgen05 kernels do not cover.  One register-tiled kernel,
+// three operand layouts:
+//   NT  Y[M,N]  = X[M,K] . W[N,K]^T (+bias, act)     BatchLinear.forward, modules.py:26-27 (+:39)
+//   NN  dX[M,K] = dZ[M,N] . W[N,K]  (* act'(Zprev))  autograd of the above (training.py:138)
+//   TN  dW[N,K]+= dZ[M,N]^T . X[M,K]  (split over M, atomics)
+#pragma once
+#include "common.cuh"
+
+namespace coordx {
+
+enum { EPI_LINEAR = 0, EPI_DX = 1, EPI_ATOMIC = 2 };
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  int M, N, K;          // C[M,N] = sum_k A(m,k) * B(k,n)
+  int64_t lda, ldb;     // leading dimension of the row-major storage of A / B
+  float* Y;             // EPI_LINEAR: activated output (nullable) | EPI_DX: output | EPI_ATOMIC: += target
+  float* Z;             // EPI_LINEAR: pre-activation output (nullable)
+  int64_t ldc;
+  const float* bias;    // EPI_LINEAR (nullable)
+  float bscale;
+  int act;              // COORDX_ACT_* or -1 (identity)
+  float S;
+  const float* Zprev;   // EPI_DX: multiply by act'(Zprev[m,n]) when non-null
+  int64_t ldz;
+  int kchunk;           // EPI_ATOMIC: K range per blockIdx.z
+};
+
+// AK : A(m,k) = A[m*lda + k]  (k contiguous)   else A[k*lda + m]
+// BKc: B(k,n) = B[n*ldb + k]  (k contiguous)   else B[k*ldb + n]
+template <int BM, int BN, int TM, int TN, bool AK, bool BKc, int EPI>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+sgemm_kernel(GemmArgs g) {
+  constexpr int BK = 8;
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int RM = TM / 4, RN = TN / 4;      // 4-wide register groups, strided over the tile
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  int kbeg = 0, kend = g.K;
+  if (EPI == EPI_ATOMIC) {
+    kbeg = blockIdx.z * g.kchunk;
+    kend = min(g.K, kbeg + g.kchunk);
+    if (kbeg >= kend) return;
+  }
+
+  constexpr int LA = (BM * BK + NT - 1) / NT, LB = (BN * BK + NT - 1) / NT;
+  float ra[LA], rb[LB];
+
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int e = tid + i * NT;
+      int r, kk;
+      if (AK) { r = e / BK; kk = e % BK; } else { kk = e / BM; r = e % BM; }
+      int m = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (e < BM * BK && m < g.M && k < kend) v = AK ? g.A[(int64_t)m * g.lda + k] : g.A[(int64_t)k * g.lda + m];
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int e = tid + i * NT;
+      int c, kk;
+      if (BKc) { c = e / BK; kk = e % BK; } else { kk = e / BN; c = e % BN; }
+      int n = n0 + c, k = k0 + kk;
+      float v = 0.f;
+      if (e < BN * BK && n < g.N && k < kend) v = BKc ? g.B[(int64_t)n * g.ldb + k] : g.B[(int64_t)k * g.ldb + n];
+      rb[i] = v;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      int e = tid + i * NT;
+      int r, kk;
+      if (AK) { r = e / BK; kk = e % BK; } else { kk = e / BM; r = e % BM; }
+      if (e < BM * BK) As[buf][kk][r] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      int e = tid + i * NT;
+      int c, kk;
+      if (BKc) { c = e / BK; kk = e % BK; } else { kk = e / BN; c = e % BN; }
+      if (e < BN * BK) Bs[buf][kk][c] = rb[i];
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  gload(kbeg);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = (k0 + BK) < kend;
+    if (more) gload(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][r * (BM / RM) + ty * 4]);
+        a[r * 4 + 0] = v.x; a[r * 4 + 1] = v.y; a[r * 4 + 2] = v.z; a[r * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int r = 0; r < RN; ++r) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][r * (BN / RN) + tx * 4]);
+        b[r * 4 + 0] = v.x; b[r * 4 + 1] = v.y; b[r * 4 + 2] = v.z; b[r * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + (i / 4) * (BM / RM) + ty * 4 + (i % 4);
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j / 4) * (BN / RN) + tx * 4 + (j % 4);
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (EPI == EPI_LINEAR) {
+        if (g.bias) v += g.bias[n] * g.bscale;
+        if (g.Z) g.Z[(int64_t)m * g.ldc + n] = v;
+        if (g.Y) g.Y[(int64_t)m * g.ldc + n] = g.act < 0 ? v : act_fwd(g.act, g.S, v);
+      } else if (EPI == EPI_DX) {
+        if (g.Zprev) v *= act_grad(g.act, g.S, g.Zprev[(int64_t)m * g.ldz + n]);
+        g.Y[(int64_t)m * g.ldc + n] = v;
+      } else {
+        atomicAdd(&g.Y[(int64_t)m * g.ldc + n], v);
+      }
+    }
+  }
+}
+
+template <bool AK, bool BKc, int EPI>
+static int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  int splits = 1;
+  GemmArgs a = g;
+  const bool big = (g.M > 64 && g.N > 64);
+  const int BM = big ? 128 : 64, BN = big ? 128 : 64;
+  dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), 1);
+  if (EPI == EPI_ATOMIC) {
+    // split the (long) reduction so the small [N,K] output still fills the chip
+    int64_t tiles = (int64_t)grid.x * grid.y;
+    splits = (int)max((int64_t)1, min(cdiv(g.K, 256), cdiv(148 * 4, tiles)));
+    a.kchunk = (int)(cdiv(cdiv(g.K, splits), 8) * 8);
+    splits = (int)cdiv(g.K, a.kchunk);
+    grid.z = splits;
+  }
+  if (big)
+    sgemm_kernel<128, 128, 8, 8, AK, BKc, EPI><<<grid, 256, 0, st>>>(a);
+  else
+    sgemm_kernel<64, 64, 4, 4, AK, BKc, EPI><<<grid, 256, 0, st>>>(a);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+// Narrow output (N <= 8: the Hd -> O final layer): one warp per row.
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+linear_narrow_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                     float bscale, int M, int N, int K, float* __restrict__ Y, float* __restrict__ Z, int64_t ldc,
+                     int act, float S) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  float acc[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+  const float* x = X + (int64_t)warp * ldx;
+  for (int k = lane; k < K; k += 32) {
+    float xv = x[k];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc[n] = fmaf(xv, W[(int64_t)n * K + k], acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    float v = acc[n];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && n < N) {
+      if (bias) v += bias[n] * bscale;
+      if (Z) Z[(int64_t)warp * ldc + n] = v;
+      if (Y) Y[(int64_t)warp * ldc + n] = act < 0 ? v : act_fwd(act, S, v);
+    }
+  }
+}
+
+// Y = act(X W^T + b*bscale); Z (pre-activation) optional.  X [M,K] (ld ldx), W [N,K].
+static int linear_forward(const float* X, int64_t ldx, const float* W, const float* bias, float bscale, int M, int N,
+                          int K, float* Y, float* Z, int64_t ldc, int act, float S, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (N <= 8) {
+    int blocks = (int)cdiv((int64_t)M * 32, 256);
+    linear_narrow_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, W, bias, bscale, M, N, K, Y, Z, ldc, act, S);
+    CX_LAUNCH_CHECK();
+    return 0;
+  }
+  GemmArgs g{};
+  g.A = X; g.lda = ldx; g.B = W; g.ldb = K; g.M = M; g.N = N; g.K = K;
+  g.Y = Y; g.Z = Z; g.ldc = ldc; g.bias = bias; g.bscale = bscale; g.act = act; g.S = S;
+  return launch_sgemm<true, true, EPI_LINEAR>(g, st);
+}
+
+// dX[M,K] = dZ[M,N] W[N,K], optionally * act'(Zprev[M,K])
+static int linear_backward_dx(const float* dZ, int64_t lddz, const float* W, int M, int N, int K, float* dX, int64_t lddx,
+                              const float* Zprev, int64_t ldz, int act, float S, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = dZ; g.lda = lddz; g.B = W; g.ldb = K; g.M = M; g.N = K; g.K = N;
+  g.Y = dX; g.ldc = lddx; g.Zprev = Zprev; g.ldz = ldz; g.act = act; g.S = S;
+  return launch_sgemm<true, false, EPI_DX>(g, st);
+}
+
+// dW[N,K] += dZ[M,N]^T X[M,K]
+static int linear_backward_dw(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int M, int N, int K, float* dW,
+                              cudaStream_t st) {
+  GemmArgs g{};
+  g.A = dZ; g.lda = lddz; g.B = X; g.ldb = ldx; g.M = N; g.N = K; g.K = M;
+  g.Y = dW; g.ldc = K;
+  return launch_sgemm<false, false, EPI_ATOMIC>(g, st);
+}
+
+// db[n] += scale * sum_m dZ[m,n]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dZ, int64_t ld, int M, int N, float scale, float* __restrict__ db, int rows_per_block) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int m = r0 + (threadIdx.x >> 5); m < r1; m += 8) s += dZ[(int64_t)m * ld + n];
+  __shared__ float red[8][33];
+  red[threadIdx.x >> 5][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    if (n < N) atomicAdd(&db[n], t * scale);
+  }
+}
+
+static int bias_backward(const float* dZ, int64_t ld, int M, int N, float scale, float* db, cudaStream_t st) {
+  if (M <= 0) return 0;
+  int rpb = 2048;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
+  colsum_kernel<<<grid, 256, 0, st>>>(dZ, ld, M, N, scale, db, rpb);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace coordx

@@ -1,0 +1,639 @@
+"""Host-side mirror of the reference's model API for the split-MLP path.
+
+Same names, constructor kwargs, attributes, `state_dict` keys and forward
+signatures as /root/reference/modules.py (SingleBVPNet :357-474, SplitFCBlock
+:132-354, BatchLinear :12-28, Sine :31-39, PosEncodingNeRF :511-576), so
+training.py / experiment_scripts/train_*.py can drive it unchanged - but the grid
+path (`coords_split`, `forward_split_channel`, `forward_split_fusion`) executes in
+libcoordx_b200.so (hand-written sm_100a CUDA behind the C ABI of
+include/coordx_b200.h).  PyTorch provides parameters, device memory, streams and
+autograd plumbing only.
+
+Not on the hot path and kept as plain torch ops (SURVEY 8f "next"): the
+scattered-point path `{'coords': ...}` (modules.py:257-309, needed by summaries and
+coordinate-gradient losses) and the un-split FCBlock baseline.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+__all__ = ['BatchLinear', 'Sine', 'FCBlock', 'SplitFCBlock', 'SingleBVPNet', 'PosEncodingNeRF',
+           'ImageDownsampling', 'sine_init', 'first_layer_sine_init', 'init_weights_normal']
+
+
+# ----------------------------------------------------------------------------- layers
+class BatchLinear(nn.Linear):
+    """modules.py:12-28: y = x W^T, then y += bias / num_input (num_input = number of
+    branches on the shared pre-fusion layers, modules.py:224-229)."""
+    num_input = 1
+
+    def forward(self, input, params=None):
+        weight = self.weight if params is None else params['weight']
+        bias = self.bias if params is None else params.get('bias', None)
+        return F.linear(input, weight) + bias / self.num_input
+
+
+class Sine(nn.Module):
+    """modules.py:31-39: sin(30 * split_scale * x)."""
+    split_scale = 1
+
+    def forward(self, input):
+        return torch.sin(30 * self.split_scale * input)
+
+
+def init_weights_normal(m):
+    if type(m) in (BatchLinear, nn.Linear) and hasattr(m, 'weight'):
+        nn.init.kaiming_normal_(m.weight, a=0.0, nonlinearity='relu', mode='fan_in')
+
+
+def sine_init(m):
+    """modules.py:639-644"""
+    with torch.no_grad():
+        if hasattr(m, 'weight'):
+            bound = np.sqrt(6 / m.weight.size(-1)) / 30
+            m.weight.uniform_(-bound, bound)
+
+
+def first_layer_sine_init(m):
+    """modules.py:647-652"""
+    with torch.no_grad():
+        if hasattr(m, 'weight'):
+            bound = 1 / m.weight.size(-1)
+            m.weight.uniform_(-bound, bound)
+
+
+_NONLINEARITIES = {
+    # name -> (factory, weight init, first-layer init)       (modules.py:171-177)
+    'sine': (Sine, sine_init, first_layer_sine_init),
+    'relu': (lambda: nn.ReLU(inplace=False), init_weights_normal, None),
+}
+
+
+def _layer(in_f, out_f, nl=None):
+    mods = [BatchLinear(in_f, out_f)]
+    if nl is not None:
+        mods.append(nl)
+    return nn.Sequential(*mods)
+
+
+# ----------------------------------------------------------------------------- C-ABI glue
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _as_f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _NetDesc:
+    """Builds `struct coordx_net` for a SplitFCBlock; keeps the tensors it points to alive."""
+
+    def __init__(self, block: 'SplitFCBlock', params, n_tables=None):
+        self.keep = []
+        n = _lib.Net()
+        # the trunk only needs the number of feature tables being fused, which may differ from the
+        # branch count when the caller pre-combined some axes (train_video.py:121-128)
+        n.n_branches = block.split_channels if n_tables is None else n_tables
+        for c, f in enumerate(block.feat_per_channel):
+            n.branch_in[c] = f
+        layers = block.layer_dims
+        n.pre_width = block.pre_width
+        n.fuse_width = block.fuse_width
+        n.hidden = block.fusion_feat_size
+        n.n_pre = block.approx_layers
+        n.n_layers = len(layers)
+        for k, (o, i) in enumerate(layers):
+            n.layer_in[k], n.layer_out[k] = i, o
+        n.act = _lib.ACT_SINE if block.nonlinearity == 'sine' else _lib.ACT_RELU
+        n.fusion_op = {'sum': _lib.FUSE_SUM, 'prod': _lib.FUSE_PROD}[block.fusion_operator]
+        n.fusion_before_act = int(block.fusion_before_act)
+        n.has_code = int(block.learn_code)
+        n.act_scale = float(block.act_scale)
+        it = iter(params)
+        for c in range(block.split_channels):
+            n.first_w[c] = self._p(next(it))
+            n.first_b[c] = self._p(next(it))
+        for k in range(len(layers)):
+            n.layer_w[k] = self._p(next(it))
+            n.layer_b[k] = self._p(next(it))
+        if block.learn_code:
+            n.code = self._p(next(it))
+        self.net = n
+
+    def _p(self, t):
+        t = _as_f32c(t)
+        if not t.is_cuda:
+            raise _lib.CoordxError('coordx_b200: parameters must live on a CUDA device (model.cuda()); '
+                                   'there is no CPU path for the split-MLP grid kernels')
+        self.keep.append(t)
+        return t.data_ptr()
+
+
+def _grads_for(block, params):
+    g = _lib.Grads()
+    bufs = [torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format) for p in params]
+    it = iter(bufs)
+    for c in range(block.split_channels):
+        g.first_w[c] = next(it).data_ptr()
+        g.first_b[c] = next(it).data_ptr()
+    for k in range(len(block.layer_dims)):
+        g.layer_w[k] = next(it).data_ptr()
+        g.layer_b[k] = next(it).data_ptr()
+    if block.learn_code:
+        g.code = next(it).data_ptr()
+    return g, bufs
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class _BranchFn(torch.autograd.Function):
+    """SplitFCBlock.forward_channel (modules.py:311-327) through coordx_branch_forward/backward."""
+
+    @staticmethod
+    def forward(ctx, block, branch, coords, *params):
+        lib = _lib.load()
+        x = _as_f32c(coords)
+        if not x.is_cuda:
+            raise _lib.CoordxError('coordx_b200: the grid path needs CUDA tensors (no CPU fallback)')
+        n = x.shape[0]
+        desc = _NetDesc(block, params)
+        feat = torch.empty(n, block.fuse_width, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 0)
+            ws = _workspace(ws_bytes, x.device)
+            _lib.check(lib.coordx_branch_forward(desc.net, branch, x.data_ptr(), n, feat.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), _stream_ptr()), 'coordx_branch_forward')
+        ctx.block, ctx.branch = block, branch
+        ctx.save_for_backward(x, *params)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        lib = _lib.load()
+        x, *params = ctx.saved_tensors
+        block, branch = ctx.block, ctx.branch
+        n = x.shape[0]
+        desc = _NetDesc(block, params)
+        grads, bufs = _grads_for(block, params)
+        d = _as_f32c(dfeat)
+        dcoords = torch.empty_like(x) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(x.device):
+            ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 1)
+            ws = _workspace(ws_bytes, x.device)
+            _lib.check(lib.coordx_branch_backward(desc.net, branch, x.data_ptr(), n, d.data_ptr(), grads,
+                                                  dcoords.data_ptr() if dcoords is not None else None,
+                                                  ws.data_ptr(), ws.numel(), _stream_ptr()), 'coordx_branch_backward')
+        used = block.branch_param_mask(branch)
+        out = [b if (u and ctx.needs_input_grad[3 + i]) else None for i, (b, u) in enumerate(zip(bufs, used))]
+        return (None, None, dcoords, *out)
+
+
+class _FusionFn(torch.autograd.Function):
+    """SplitFCBlock.forward_fusion (modules.py:329-354) through coordx_trunk_forward/backward.
+    feats: C tables [N_c, F]; returns [prod N_c, out_width]."""
+
+    @staticmethod
+    def forward(ctx, block, precision, nfeat, *tensors):
+        lib = _lib.load()
+        feats = [_as_f32c(t) for t in tensors[:nfeat]]
+        params = tensors[nfeat:]
+        dev = feats[0].device
+        if not dev.type == 'cuda':
+            raise _lib.CoordxError('coordx_b200: the grid path needs CUDA tensors (no CPU fallback)')
+        ns = [f.shape[0] for f in feats]
+        desc = _NetDesc(block, params, n_tables=nfeat)
+        prec = block.resolve_precision(desc.net, precision)
+        P = int(np.prod(ns))
+        out = torch.empty(P, block.out_width, dtype=torch.float32, device=dev)
+        n_arr = _lib.i64_array(ns)
+        f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
+        with torch.cuda.device(dev):
+            ws_bytes = lib.coordx_trunk_workspace_bytes(desc.net, n_arr, 0, ns[0], prec, 0)
+            ws = _workspace(ws_bytes, dev)
+            _lib.check(lib.coordx_trunk_forward(desc.net, f_arr, n_arr, 0, ns[0], out.data_ptr(), prec, ws.data_ptr(),
+                                                ws.numel(), _stream_ptr()), 'coordx_trunk_forward')
+        ctx.block, ctx.prec, ctx.nfeat = block, prec, nfeat
+        ctx.save_for_backward(*feats, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        block, nfeat = ctx.block, ctx.nfeat
+        feats = list(ctx.saved_tensors[:nfeat])
+        params = ctx.saved_tensors[nfeat:]
+        dev = feats[0].device
+        ns = [f.shape[0] for f in feats]
+        desc = _NetDesc(block, params, n_tables=nfeat)
+        grads, bufs = _grads_for(block, params)
+        d = _as_f32c(dout)
+        dfeats = [torch.zeros_like(f) for f in feats]
+        n_arr = _lib.i64_array(ns)
+        f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
+        df_arr = _lib.ptr_array([f.data_ptr() for f in dfeats])
+        with torch.cuda.device(dev):
+            ws_bytes = lib.coordx_trunk_workspace_bytes(desc.net, n_arr, 0, ns[0], ctx.prec, 1)
+            ws = _workspace(ws_bytes, dev)
+            _lib.check(lib.coordx_trunk_backward(desc.net, f_arr, n_arr, 0, ns[0], d.data_ptr(), grads, df_arr, ctx.prec,
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr()), 'coordx_trunk_backward')
+        used = block.trunk_param_mask()
+        pg = [b if (u and ctx.needs_input_grad[3 + nfeat + i]) else None for i, (b, u) in enumerate(zip(bufs, used))]
+        fg = [df if ctx.needs_input_grad[3 + i] else None for i, df in enumerate(dfeats)]
+        return (None, None, None, *fg, *pg)
+
+
+# ----------------------------------------------------------------------------- blocks
+class FCBlock(nn.Module):
+    """Un-split MLP baseline (modules.py:42-129) - plain torch ops, off the hot path."""
+
+    def __init__(self, in_features, out_features, num_hidden_layers, hidden_features, outermost_linear=False,
+                 nonlinearity='relu', weight_init=None, approx_layers=2, fusion_size=1, reduced=False):
+        super().__init__()
+        factory, nl_init, first_init = _NONLINEARITIES[nonlinearity]
+        nl = factory()
+        self.weight_init = weight_init if weight_init is not None else nl_init
+        s = 1 if reduced else fusion_size
+        in_size = out_size = hidden_features * s
+        layers = [_layer(in_features, out_size, nl)]
+        for i in range(num_hidden_layers):
+            if i + 1 == approx_layers:
+                out_size = hidden_features if not reduced else hidden_features * fusion_size
+            if i == approx_layers:
+                out_size = hidden_features
+            layers.append(_layer(in_size, out_size, nl))
+            in_size = out_size
+        layers.append(_layer(in_size, out_features, None if outermost_linear else nl))
+        self.net = nn.Sequential(*layers)
+        self.net.apply(self.weight_init)
+        if first_init is not None:
+            self.net[0].apply(first_init)
+
+    def forward(self, coords, params=None, **kwargs):
+        return self.net(coords)
+
+
+class SplitFCBlock(nn.Module):
+    """modules.py:132-354.  Same constructor / attributes / parameter names; the grid path
+    runs in libcoordx_b200.so."""
+
+    def __init__(self, in_features, out_features, num_hidden_layers, hidden_features, outermost_linear=False,
+                 nonlinearity='relu', weight_init=None, coord_dim=2, approx_layers=2, split_rule=None,
+                 fusion_operator='sum', act_scale=1, fusion_before_act=False, use_atten=False, learn_code=False,
+                 last_layer_features=-1, fusion_size=1, reduced=False, precision='auto'):
+        super().__init__()
+        if nonlinearity not in _NONLINEARITIES:
+            raise KeyError(nonlinearity)                       # modules.py:179
+        if fusion_operator not in ('sum', 'prod'):
+            # the reference silently skips the fusion for unknown strings (modules.py:336-341)
+            raise ValueError(f"fusion_operator must be 'sum' or 'prod', got {fusion_operator!r}")
+        if not outermost_linear:
+            raise NotImplementedError('coordx_b200 covers outermost_linear=True (what SingleBVPNet builds, modules.py:406)')
+        if use_atten:
+            raise NotImplementedError('use_atten is ignored by the reference grid path and is out of scope here')
+        self.first_layer_init = None
+        self.coord_dim = coord_dim
+        per = in_features // coord_dim
+        self.feat_per_channel = [per] * coord_dim if split_rule is None else [per * k for k in split_rule]
+        self.split_channels = len(self.feat_per_channel)
+        if self.split_channels > _lib.MAX_BRANCHES:
+            raise ValueError('too many branches')
+        self.approx_layers = approx_layers
+        self.num_hidden_layers = num_hidden_layers
+        self.module_prefix = ""
+        self.fusion_operator = fusion_operator
+        self.fusion_before_act = fusion_before_act
+        self.out_features = out_features
+        self.use_atten = use_atten
+        self.learn_code = learn_code
+        self.nonlinearity = nonlinearity
+        self.act_scale = act_scale
+        self.precision = precision
+        self.fusion_size = 1
+        self.fusion_feat_size = out_features
+        if approx_layers != num_hidden_layers + 1:
+            last_layer_features = 1
+            self.fusion_size = fusion_size
+            self.fusion_feat_size = hidden_features
+        elif last_layer_features < 0:
+            last_layer_features = hidden_features
+        last_layer_features = last_layer_features * out_features
+
+        factory, nl_init, first_init = _NONLINEARITIES[nonlinearity]
+        nl = factory()
+        self.weight_init = weight_init if weight_init is not None else nl_init
+
+        s = 1 if reduced else fusion_size
+        self.pre_width = hidden_features * s
+        self.coord_linears = nn.ModuleList([BatchLinear(f, self.pre_width) for f in self.feat_per_channel])
+        self.coord_nl = nl
+        self.coord_nl.split_scale = act_scale
+        self.coord_linears.apply(first_init if first_init is not None else self.weight_init)
+
+        dims = []                                              # (out, in) of net[k]
+        n_shared = max(min(approx_layers, num_hidden_layers) - 1, 0)
+        dims += [(self.pre_width, self.pre_width)] * n_shared
+        dims.append((hidden_features * fusion_size, self.pre_width))
+        dims += [(hidden_features, hidden_features)] * (num_hidden_layers - n_shared - 1)
+        dims.append((last_layer_features, hidden_features))
+        self.layer_dims = dims
+        self.net = nn.Sequential(*[_layer(i, o, nl if k < len(dims) - 1 else None) for k, (o, i) in enumerate(dims)])
+        if self.weight_init is not None:
+            self.net.apply(self.weight_init)
+        for k in range(min(approx_layers, len(dims))):
+            self.net[k][0].num_input = self.split_channels
+        if learn_code:
+            self.code = nn.Parameter(torch.ones(hidden_features * fusion_size))
+        self.fuse_width = dims[approx_layers - 1][0] if approx_layers > 0 else self.pre_width
+        self.out_width = last_layer_features
+        if len(dims) > _lib.MAX_LAYERS:
+            raise ValueError('too many layers')
+
+    # ---- parameter plumbing ------------------------------------------------------
+    def abi_params(self):
+        ps = []
+        for lin in self.coord_linears:
+            ps += [lin.weight, lin.bias]
+        for seq in self.net:
+            ps += [seq[0].weight, seq[0].bias]
+        if self.learn_code:
+            ps.append(self.code)
+        return ps
+
+    def branch_param_mask(self, branch):
+        m = []
+        for c in range(self.split_channels):
+            m += [c == branch] * 2
+        for k in range(len(self.layer_dims)):
+            m += [k < self.approx_layers] * 2
+        if self.learn_code:
+            m.append(False)
+        return m
+
+    def trunk_param_mask(self):
+        m = [False] * (2 * self.split_channels)
+        for k in range(len(self.layer_dims)):
+            m += [k >= self.approx_layers] * 2
+        if self.learn_code:
+            m.append(True)
+        return m
+
+    def resolve_precision(self, net, precision=None):
+        p = precision or self.precision or 'auto'
+        if p == 'auto':
+            p = os.environ.get('COORDX_PRECISION', 'auto')
+        lib = _lib.load()
+        if p == 'auto':
+            return _lib.PREC_BF16 if lib.coordx_trunk_tc_supported(net, _lib.PREC_BF16) else _lib.PREC_FP32
+        code = _lib.PRECISIONS[p]
+        if code != _lib.PREC_FP32 and not lib.coordx_trunk_tc_supported(net, code):
+            raise _lib.CoordxError(f'precision={p!r}: the tcgen05 trunk kernel does not cover this architecture '
+                                   '(needs hidden_features=256, one hidden trunk layer, fusion_size=1); use fp32/auto')
+        return code
+
+    # ---- the hot path ------------------------------------------------------------
+    def forward_channel(self, coord, channel_id, pos_codes=None):
+        """modules.py:311-327.  coord [..., f_c] -> [..., F]"""
+        lead = coord.shape[:-1]
+        h = _BranchFn.apply(self, channel_id, coord.reshape(-1, coord.shape[-1]), *self.abi_params())
+        h = h.reshape(*lead, h.shape[-1])
+        if pos_codes is not None and self.approx_layers > 0:
+            h = h + pos_codes
+        return h
+
+    def forward_fusion(self, hs, precision=None):
+        """modules.py:329-354.  hs: iterable of broadcastable feature tensors [..., F]."""
+        hs = list(hs)
+        plan = _broadcast_axes([tuple(h.shape[:-1]) for h in hs])
+        if plan is None:
+            return self._fusion_eager(hs)
+        order, ns, out_lead = plan
+        feats = [hs[i].reshape(-1, hs[i].shape[-1]) for i in order]
+        if len(feats) < 2 or len(feats) > _lib.MAX_BRANCHES:
+            return self._fusion_eager(hs)
+        out = _FusionFn.apply(self, precision, len(feats), *feats, *self.abi_params())
+        return out.reshape(*out_lead, out.shape[-1])
+
+    def _fusion_eager(self, hs):
+        """Broadcast patterns that are not an outer product of per-tensor axes (e.g. a shared
+        batch dimension > 1): plain torch ops, as the reference."""
+        h = hs[0]
+        for hi in hs[1:]:
+            h = h + hi if self.fusion_operator == 'sum' else h * hi
+        if self.fusion_before_act:
+            h = self.net[self.approx_layers - 1][1](h)
+        if self.learn_code:
+            h = h * self.code
+        if h.shape[-1] > self.fusion_feat_size:
+            h = h.reshape(*h.shape[:-1], self.fusion_feat_size, -1).sum(-1)
+        for k in range(self.approx_layers, self.num_hidden_layers + 1):
+            h = self.net[k](h)
+        return h
+
+    def forward(self, coords, params=None, pos_codes=None, split_coord=False, ret_feat=False, **kwargs):
+        if split_coord:                                        # modules.py:248-255
+            hs = [self.forward_channel(coord, i, pos_codes) for i, coord in enumerate(coords)]
+            h = self.forward_fusion(hs)
+            out = h.reshape(h.shape[0], -1, h.shape[-1])
+            return (out, hs) if ret_feat else out
+        return self._forward_scattered(coords, pos_codes, ret_feat)
+
+    def _forward_scattered(self, coords, pos_codes=None, ret_feat=False):
+        """Arbitrary points [..., sum f_c] (modules.py:257-309) - torch ops, differentiable
+        w.r.t. coords (diff_operators.gradient, utils.write_image_summary)."""
+        al = self.approx_layers
+        parts = torch.split(coords, self.feat_per_channel, dim=-1)
+        hs = torch.stack([lin(x) for lin, x in zip(self.coord_linears, parts)], -2)
+        hs = self.coord_nl(hs)
+        for k in range(al - 1):
+            hs = self.net[k](hs)
+        if al > 0:
+            hs = self.net[al - 1][0](hs) if self.fusion_before_act else self.net[al - 1](hs)
+        if pos_codes is not None:
+            hs = hs + pos_codes
+        h = hs.sum(-2) if self.fusion_operator == 'sum' else hs.prod(-2)
+        if self.fusion_before_act:
+            h = self.net[al - 1][1](h)
+        if self.learn_code:
+            h = h * self.code
+        h = h.reshape(*h.shape[:-1], self.fusion_feat_size, -1).sum(-1)
+        for k in range(al, self.num_hidden_layers + 1):
+            h = self.net[k](h)
+        return (h, hs) if ret_feat else h
+
+
+def _broadcast_axes(shapes):
+    """Decide whether broadcasting the given leading shapes is an outer product in which every
+    tensor owns a disjoint, contiguous run of output dims.  Returns (tensor order, axis lengths,
+    output leading shape) or None."""
+    nd = max((len(s) for s in shapes), default=0)
+    padded = [(1,) * (nd - len(s)) + tuple(s) for s in shapes]
+    out_lead = [1] * nd
+    owner = [None] * nd
+    spans = []
+    for t, s in enumerate(padded):
+        dims = [d for d in range(nd) if s[d] != 1]
+        for d in dims:
+            if owner[d] is not None:
+                return None
+            owner[d] = t
+            out_lead[d] = s[d]
+        if dims and dims != list(range(dims[0], dims[-1] + 1)):
+            return None
+        spans.append((dims[0] if dims else -1, t, int(np.prod([s[d] for d in dims])) if dims else 1))
+    spans.sort()
+    order = [t for _, t, _ in spans]
+    ns = [n for _, _, n in spans]
+    return order, ns, out_lead
+
+
+# ----------------------------------------------------------------------------- model
+class ImageDownsampling(nn.Module):
+    """modules.py:477-508; never enabled by any script (downsample=False everywhere)."""
+
+    def __init__(self, sidelength, downsample=False):
+        super().__init__()
+        self.sidelength = (sidelength, sidelength) if isinstance(sidelength, int) else sidelength
+        if self.sidelength is None:
+            assert downsample is False
+        if downsample:
+            raise NotImplementedError('downsample=True is out of scope')
+        self.downsample = downsample
+
+    def forward(self, coords):
+        return coords
+
+
+class PosEncodingNeRF(nn.Module):
+    """modules.py:511-576: [x, sin(f_k x), cos(f_k x)]_k, per-axis contiguous when freq_last."""
+
+    def __init__(self, in_features, sidelength=None, fn_samples=None, use_nyquist=True, freq_last=False,
+                 freq_params=None, include_coord=True):
+        super().__init__()
+        self.in_features = in_features
+        self.freq_last = freq_last
+        self.include_coord = include_coord
+        if freq_params is None:
+            if in_features == 3:
+                self.num_frequencies = 10
+            elif in_features == 2:
+                assert sidelength is not None
+                if isinstance(sidelength, int):
+                    sidelength = (sidelength, sidelength)
+                self.num_frequencies = self.get_num_frequencies_nyquist(min(sidelength)) if use_nyquist else 4
+            elif in_features == 1:
+                if fn_samples is None:
+                    fn_samples = min(sidelength[0], sidelength[1])
+                self.num_frequencies = self.get_num_frequencies_nyquist(fn_samples) if use_nyquist else 4
+            else:
+                raise ValueError(in_features)
+            bands = 2 ** torch.arange(self.num_frequencies) * np.pi
+        else:
+            self.num_frequencies = int(freq_params[1])
+            bands = 2 * (2. ** torch.linspace(0, freq_params[0], self.num_frequencies) - 1) * np.pi
+        self.out_dim = in_features * (2 * self.num_frequencies + (1 if include_coord else 0))
+        self.freq_bands = nn.Parameter(bands.float(), requires_grad=False)
+
+    @staticmethod
+    def get_num_frequencies_nyquist(samples):
+        return int(math.floor(math.log(1 / (2 * (2 * 1 / samples)), 2)))
+
+    def forward(self, coords, single_channel=False):
+        f = coords.shape[-1] if single_channel else self.in_features
+        ang = coords.unsqueeze(-2) * self.freq_bands.reshape([1] * (coords.dim() - 1) + [-1, 1])
+        enc = torch.cat([torch.sin(ang), torch.cos(ang)], -1).flatten(-2)
+        if self.include_coord:
+            enc = torch.cat([coords, enc], -1)
+        if self.freq_last:
+            lead = enc.shape[:-1]
+            enc = enc.reshape(*lead, -1, f).transpose(-1, -2).reshape(*lead, -1)
+        return enc
+
+
+class SingleBVPNet(nn.Module):
+    """modules.py:357-474.  `precision` ('auto' | 'fp32' | 'bf16' | 'fp16') and `quiet` are the
+    only additions to the reference kwargs."""
+
+    def __init__(self, out_features=1, type='sine', in_features=2, mode='mlp', hidden_features=256,
+                 num_hidden_layers=3, split_mlp=False, split_rule=None, pos_enc=False, **kwargs):
+        super().__init__()
+        quiet = kwargs.pop('quiet', False)
+        precision = kwargs.pop('precision', 'auto')
+        if not quiet:
+            print(kwargs)
+        self.mode = mode
+        self.split_mlp = split_mlp
+        self.pos_enc = pos_enc
+        self.module_prefix = ""
+        coord_dim = in_features
+        if mode == 'nerf':
+            self.positional_encoding = PosEncodingNeRF(in_features=in_features, sidelength=kwargs.get('sidelength', None),
+                                                       fn_samples=kwargs.get('fn_samples', None),
+                                                       use_nyquist=kwargs.get('use_nyquist', True),
+                                                       freq_params=kwargs.get('freq_params', None),
+                                                       include_coord=kwargs.get('include_coord', True),
+                                                       freq_last=split_mlp)
+            in_features = self.positional_encoding.out_dim
+        elif mode != 'mlp':
+            raise NotImplementedError(f"mode={mode!r} is outside the split-MLP hot path (SURVEY 2: RBFLayer out of scope)")
+        if pos_enc:
+            raise NotImplementedError('pos_enc encoder is not reachable from coords_split and is out of scope')
+        self.image_downsampling = ImageDownsampling(sidelength=kwargs.get('sidelength', None),
+                                                    downsample=kwargs.get('downsample', False))
+        if not split_mlp:
+            self.net = FCBlock(in_features=in_features, out_features=out_features, num_hidden_layers=num_hidden_layers,
+                               hidden_features=hidden_features, outermost_linear=True, nonlinearity=type,
+                               approx_layers=kwargs.get('approx_layers', 2), fusion_size=kwargs.get('fusion_size', 1),
+                               reduced=kwargs.get('reduced', False))
+        else:
+            self.net = SplitFCBlock(in_features=in_features, out_features=out_features,
+                                    num_hidden_layers=num_hidden_layers, hidden_features=hidden_features,
+                                    outermost_linear=True, nonlinearity=type, coord_dim=coord_dim, split_rule=split_rule,
+                                    approx_layers=kwargs.get('approx_layers', 2), act_scale=kwargs.get('act_scale', 1),
+                                    fusion_operator=kwargs.get('fusion_operator', 'prod'),
+                                    fusion_before_act=kwargs.get('fusion_before_act', False),
+                                    use_atten=kwargs.get('use_atten', False), learn_code=kwargs.get('learn_code', False),
+                                    last_layer_features=kwargs.get('last_layer_features', -1),
+                                    fusion_size=kwargs.get('fusion_size', 1), reduced=kwargs.get('reduced', False),
+                                    precision=precision)
+        if not quiet:
+            print(self)
+
+    def forward(self, model_input, params=None, ret_feat=False):
+        """dict in / dict out (modules.py:419-454); if both keys are present the split result wins."""
+        coords_org = output = None
+        if 'coords' in model_input:
+            coords_org = model_input['coords'].clone().detach().requires_grad_(True)
+            coords = coords_org
+            if self.mode == 'nerf':
+                coords = self.positional_encoding(coords)
+            output = self.net(coords)
+        if 'coords_split' in model_input:
+            coords_org = [c.clone().detach().requires_grad_(True) for c in model_input['coords_split']]
+            coords = coords_org
+            if self.mode == 'nerf':
+                coords = [self.positional_encoding(c, single_channel=True) for c in coords]
+            output = self.net(coords, split_coord=True, ret_feat=ret_feat)
+        return {'model_in': coords_org, 'model_out': output}
+
+    def forward_split_channel(self, coord, channel_id):
+        """modules.py:463-470"""
+        if not self.split_mlp:
+            return None
+        if self.mode == 'nerf':
+            coord = self.positional_encoding(coord, single_channel=True)
+        return self.net.forward_channel(coord, channel_id)
+
+    def forward_split_fusion(self, h):
+        """modules.py:472-474"""
+        return self.net.forward_fusion(h)
