@@ -67,6 +67,9 @@ _PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     'coordx_abi_version': (C.c_int, []),
     'coordx_last_error': (C.c_char_p, []),
+    'coordx_launch_count': (C.c_ulonglong, []),
+    'coordx_profile_enable': (C.c_int, [C.c_int]),
+    'coordx_profile_last_ms': (C.c_int, [C.POINTER(C.c_float)]),
     'coordx_trunk_tc_supported': (C.c_int, [C.POINTER(Net), C.c_int]),
     'coordx_branch_workspace_bytes': (C.c_size_t, [C.POINTER(Net), C.c_int, C.c_int64, C.c_int]),
     'coordx_branch_forward': (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -12,6 +12,7 @@
 namespace coordx {
 
 extern thread_local char g_err[512];
+extern unsigned long long g_launches;     // kernels launched by this library (bench.py's gpu_launches)
 
 inline int set_err(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
   snprintf(g_err, sizeof(g_err), fmt, a, b, c);
@@ -28,7 +29,11 @@ inline int set_err(int code, const char* fmt, const char* a = "", long long b = 
     }                                                                                      \
   } while (0)
 
-#define CX_LAUNCH_CHECK() CX_CUDA(cudaGetLastError())
+#define CX_LAUNCH_CHECK()          \
+  do {                             \
+    ++coordx::g_launches;          \
+    CX_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define CX_TRY(expr)          \
   do {                        \

@@ -8,6 +8,7 @@
 namespace coordx {
 
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 struct Layer {
   const float* W;
@@ -168,6 +169,21 @@ extern "C" {
 
 int coordx_abi_version(void) { return COORDX_ABI_VERSION; }
 const char* coordx_last_error(void) { return g_err; }
+
+unsigned long long coordx_launch_count(void) { return g_launches; }
+
+int coordx_profile_enable(int on) {
+  tc::g_profile = on != 0;
+  return 0;
+}
+
+// milliseconds of the last profiled trunk kernel (synchronises on its end event)
+int coordx_profile_last_ms(float* ms_host) {
+  if (!ms_host || !tc::g_prof_ev[0]) return set_err(COORDX_ERR_ARG, "no profiled launch%s");
+  CX_CUDA(cudaEventSynchronize(tc::g_prof_ev[1]));
+  CX_CUDA(cudaEventElapsedTime(ms_host, tc::g_prof_ev[0], tc::g_prof_ev[1]));
+  return 0;
+}
 
 int coordx_trunk_tc_supported(const coordx_net* net, int precision) {
   if (check_net(net) != 0) return 0;

@@ -370,6 +370,10 @@ static FwdPlan plan_fwd(int64_t n_inner) {
   return pl;
 }
 
+// optional device timing of the main kernel alone (bench.py roofline)
+static bool g_profile = false;
+static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+
 template <typename T, int OP, int ACT, int O>
 static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
   auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O>;
@@ -378,8 +382,16 @@ static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
     CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
     attr_done = true;
   }
+  if (g_profile) {
+    if (!g_prof_ev[0]) {
+      CX_CUDA(cudaEventCreate(&g_prof_ev[0]));
+      CX_CUDA(cudaEventCreate(&g_prof_ev[1]));
+    }
+    CX_CUDA(cudaEventRecord(g_prof_ev[0], st));
+  }
   kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);
   CX_LAUNCH_CHECK();
+  if (g_profile) CX_CUDA(cudaEventRecord(g_prof_ev[1], st));
   return 0;
 }
 

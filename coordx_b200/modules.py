@@ -355,7 +355,8 @@ class SplitFCBlock(nn.Module):
         if learn_code:
             self.code = nn.Parameter(torch.ones(hidden_features * fusion_size))
         self.fuse_width = dims[approx_layers - 1][0] if approx_layers > 0 else self.pre_width
-        self.out_width = last_layer_features
+        # approx_layers == num_hidden_layers + 1: no trunk, the group-sum of modules.py:349-351 is the output
+        self.out_width = last_layer_features if approx_layers < len(dims) else self.fusion_feat_size
         if len(dims) > _lib.MAX_LAYERS:
             raise ValueError('too many layers')
 
@@ -394,7 +395,10 @@ class SplitFCBlock(nn.Module):
             p = os.environ.get('COORDX_PRECISION', 'auto')
         lib = _lib.load()
         if p == 'auto':
-            return _lib.PREC_BF16 if lib.coordx_trunk_tc_supported(net, _lib.PREC_BF16) else _lib.PREC_FP32
+            # SIREN activations live in [-1, 1]: bf16 operands meet the 2e-3 output bar; ReLU nets are
+            # unnormalised, fp16's 3 extra mantissa bits are needed there (tests/test_gpu_parity.py)
+            want = _lib.PREC_BF16 if self.nonlinearity == 'sine' else _lib.PREC_FP16
+            return want if lib.coordx_trunk_tc_supported(net, want) else _lib.PREC_FP32
         code = _lib.PRECISIONS[p]
         if code != _lib.PREC_FP32 and not lib.coordx_trunk_tc_supported(net, code):
             raise _lib.CoordxError(f'precision={p!r}: the tcgen05 trunk kernel does not cover this architecture '

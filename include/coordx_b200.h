@@ -87,6 +87,11 @@ typedef struct coordx_grads {
 
 int coordx_abi_version(void);
 const char* coordx_last_error(void);
+/* measurement hooks (bench.py): number of kernels this library has launched; CUDA-event timing of
+ * the dominant (tcgen05 trunk) kernel alone, on the stream it was launched on. */
+unsigned long long coordx_launch_count(void);
+int coordx_profile_enable(int on);
+int coordx_profile_last_ms(float* ms_host);
 /* 1 if the tcgen05 trunk kernels cover this architecture at `precision`. */
 int coordx_trunk_tc_supported(const coordx_net* net, int precision);
 
