@@ -4,6 +4,7 @@
 #include "elementwise.cuh"
 #include "gemm_f32.cuh"
 #include "trunk_tc.cuh"
+#include "trunk_bwd_tc.cuh"
 
 namespace coordx {
 
@@ -239,8 +240,9 @@ int coordx_branch_backward(const coordx_net* net, int branch, const float* coord
 size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t row_begin, int64_t row_end,
                                     int precision, int backward) {
   if (check_net(net) != 0 || !n) return 0;
-  if (precision != COORDX_PREC_FP32 && !backward) {
+  if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return 0;
+    if (backward) return tcb::plan_bwd(net, n, row_begin, row_end).total + 1024;
     return tc::plan_fwd(n[net->n_branches - 1]).total + 1024;
   }
   const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
@@ -297,8 +299,18 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
   if (!feats || !n || !dout || !grads || !dfeat) return set_err(COORDX_ERR_ARG, "null argument%s");
   if (row_begin < 0 || row_end > n[0] || row_begin > row_end) return set_err(COORDX_ERR_ARG, "bad slab%s [%lld, %lld)", "", row_begin, row_end);
   if (row_begin == row_end) return 0;
-  (void)precision;   // round 1: the backward always runs the FP32 kernels
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision != COORDX_PREC_FP32) {
+    if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
+    const int Lf = net->n_layers - 1;
+    int64_t pts = row_end - row_begin;
+    for (int c = 1; c < net->n_branches; ++c) pts *= n[c];
+    // gradient of the final bias: column sums of dout
+    CX_TRY(bias_backward(dout, net->layer_out[Lf], (int)pts, net->layer_out[Lf], 1.f, grads->layer_b[Lf], st));
+    if (precision == COORDX_PREC_BF16)
+      return tcb::trunk_backward_tc_t<__nv_bfloat16>(net, feats, n, row_begin, row_end, dout, grads, dfeat, ws, ws_bytes, st);
+    return tcb::trunk_backward_tc_t<__half>(net, feats, n, row_begin, row_end, dout, grads, dfeat, ws, ws_bytes, st);
+  }
   const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
   Layer L[COORDX_MAX_LAYERS + 1];
   const int nl = trunk_layers(net, grads, L);

@@ -157,7 +157,9 @@ static int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   int splits = 1;
   GemmArgs a = g;
-  const bool big = (g.M > 64 && g.N > 64);
+  // 128x128 tiles only when they still give every SM a CTA; small problems (the per-axis
+  // branch layers: M = N_c <= a few thousand rows) get 4x more 64x64 CTAs instead
+  const bool big = (g.M > 64 && g.N > 64) && (EPI == EPI_ATOMIC || cdiv(g.M, 128) * cdiv(g.N, 128) >= 148);
   const int BM = big ? 128 : 64, BN = big ? 128 : 64;
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), 1);
   if (EPI == EPI_ATOMIC) {

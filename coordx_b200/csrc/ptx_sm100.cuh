@@ -109,9 +109,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
          | (2ull << 61);                                         /* SWIZZLE_128B */
 }
 
-// kind::f16 instruction descriptor: D fp32, A/B `fmt` (0 = f16, 1 = bf16), both K-major
-__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// The SAME 8-row x 128-byte swizzle atoms read as an MN-major operand: the 64 contiguous
+// elements of a row are the M/N index, rows are the K index (8-row groups SBO = 1024 B apart);
+// further blocks of 64 M/N elements are `lbo_bytes` apart.  One UMMA_K = 16 step is two row
+// groups: advance the start address by 2048 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B `fmt` (0 = f16, 1 = bf16); a_mn / b_mn = 1
+// selects the MN-major ("transposed") form of that operand
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn = 0,
+                                                      uint32_t b_mn = 0) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // byte offset of element (row, k) inside a [rows x 64] 16-bit SWIZZLE_128B K-major chunk

@@ -312,11 +312,10 @@ trunk_fwd_tc_kernel(const FwdParams p) {
       float acc[O];
 #pragma unroll
       for (int oo = 0; oo < O; ++oo) acc[oo] = 0.f;
-#pragma unroll
-      for (int cb = 0; cb < HD / 32; ++cb) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(taddr + cb * 32, r);
-        ptx::tmem_ld_wait();
+      // TMEM -> registers double-buffered: the load of column batch cb+1 is in flight while
+      // batch cb goes through bias + sin/relu + the Hd -> O dot product
+      uint32_t ra[32], rb[32];
+      auto consume = [&](const uint32_t (&r)[32], int cb) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int k = cb * 32 + i;
@@ -329,6 +328,16 @@ trunk_fwd_tc_kernel(const FwdParams p) {
 #pragma unroll
           for (int oo = 0; oo < O; ++oo) acc[oo] = fmaf(h, c_epi.wf[oo][k], acc[oo]);
         }
+      };
+      ptx::tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll
+      for (int cb = 0; cb < HD / 32; cb += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, rb);
+        consume(ra, cb);
+        ptx::tmem_ld_wait();
+        if (cb + 2 < HD / 32) ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
+        consume(rb, cb + 1);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_tempty + 8 * e);
