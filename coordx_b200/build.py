@@ -1,42 +1,78 @@
 """Build libcoordx_b200.so (the C-ABI library of include/coordx_b200.h) in-tree with nvcc
-for sm_100a.  `python -m coordx_b200.build` or `__graft_entry__.build()`."""
+for sm_100a.  `python -m coordx_b200.build` or `__graft_entry__.build()`.
+
+Three translation units compiled in parallel and linked into one shared library:
+  coordx_abi.cu     C ABI + the FP32 (FFMA) kernels
+  trunk_fwd_tc.cu   tcgen05 fused fusion+trunk forward (CTA pair)
+  trunk_bwd_tc.cu   tcgen05 fused trunk backward
+"""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, 'csrc', 'coordx_abi.cu')
+CSRC = os.path.join(HERE, 'csrc')
+OBJ = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libcoordx_b200.so')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'csrc'))] + \
-       [os.path.join(os.path.dirname(HERE), 'include', 'coordx_b200.h')]
+UNITS = ['coordx_abi.cu', 'trunk_fwd_tc.cu', 'trunk_bwd_tc.cu']
+HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cuh', '.h'))] + \
+          [os.path.join(os.path.dirname(HERE), 'include', 'coordx_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared', '-Xptxas', '-v', '--expt-relaxed-constexpr']
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    return any(_stale(os.path.join(OBJ, u[:-3] + '.o'), [os.path.join(CSRC, u)] + HEADERS) for u in UNITS) or \
+        _stale(LIB, [os.path.join(OBJ, u[:-3] + '.o') for u in UNITS if os.path.exists(os.path.join(OBJ, u[:-3] + '.o'))])
+
+
+def _compile(nvcc, unit):
+    src, obj = os.path.join(CSRC, unit), os.path.join(OBJ, unit[:-3] + '.o')
+    if not _stale(obj, [src] + HEADERS):
+        return unit, 0, ''
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ['-c', '-o', obj, src], capture_output=True, text=True)
+    return unit, r.returncode, r.stdout + r.stderr
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB, SRC]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for u in UNITS:
+            o = os.path.join(OBJ, u[:-3] + '.o')
+            if os.path.exists(o):
+                os.remove(o)
+    with ThreadPoolExecutor(len(UNITS)) as ex:
+        results = list(ex.map(lambda u: _compile(nvcc, u), UNITS))
+    log = []
+    for unit, rc, out in results:
+        log.append(f'==== {unit}\n{out}')
+        if rc != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f'nvcc failed on {unit}')
+    objs = [os.path.join(OBJ, u[:-3] + '.o') for u in UNITS]
+    r = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs,
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError('nvcc failed building libcoordx_b200.so')
-    log = os.path.join(HERE, 'csrc', 'ptxas.log')
-    with open(log, 'w') as f:
-        f.write(r.stderr)
+        raise RuntimeError('nvcc failed linking libcoordx_b200.so')
+    with open(os.path.join(OBJ, 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
     if verbose:
-        print(r.stderr)
+        print('\n'.join(log))
     return LIB
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose=True))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

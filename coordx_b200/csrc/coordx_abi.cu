@@ -3,8 +3,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_f32.cuh"
-#include "trunk_tc.cuh"
-#include "trunk_bwd_tc.cuh"
+#include "tc_common.cuh"
 
 namespace coordx {
 
@@ -174,16 +173,13 @@ const char* coordx_last_error(void) { return g_err; }
 unsigned long long coordx_launch_count(void) { return g_launches; }
 
 int coordx_profile_enable(int on) {
-  tc::g_profile = on != 0;
+  tc::profile_enable(on != 0);
   return 0;
 }
 
 // milliseconds of the last profiled trunk kernel (synchronises on its end event)
 int coordx_profile_last_ms(float* ms_host) {
-  if (!ms_host || !tc::g_prof_ev[0]) return set_err(COORDX_ERR_ARG, "no profiled launch%s");
-  CX_CUDA(cudaEventSynchronize(tc::g_prof_ev[1]));
-  CX_CUDA(cudaEventElapsedTime(ms_host, tc::g_prof_ev[0], tc::g_prof_ev[1]));
-  return 0;
+  return tc::profile_last_ms(ms_host);
 }
 
 int coordx_trunk_tc_supported(const coordx_net* net, int precision) {
@@ -242,8 +238,8 @@ size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int
   if (check_net(net) != 0 || !n) return 0;
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return 0;
-    if (backward) return tcb::plan_bwd(net, n, row_begin, row_end).total + 1024;
-    return tc::plan_fwd(n[net->n_branches - 1]).total + 1024;
+    if (backward) return tc::bwd_workspace_bytes(net, n, row_begin, row_end) + 1024;
+    return tc::fwd_workspace_bytes(n[net->n_branches - 1]) + 1024;
   }
   const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
   Layer L[COORDX_MAX_LAYERS + 1];
@@ -307,9 +303,7 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
     for (int c = 1; c < net->n_branches; ++c) pts *= n[c];
     // gradient of the final bias: column sums of dout
     CX_TRY(bias_backward(dout, net->layer_out[Lf], (int)pts, net->layer_out[Lf], 1.f, grads->layer_b[Lf], st));
-    if (precision == COORDX_PREC_BF16)
-      return tcb::trunk_backward_tc_t<__nv_bfloat16>(net, feats, n, row_begin, row_end, dout, grads, dfeat, ws, ws_bytes, st);
-    return tcb::trunk_backward_tc_t<__half>(net, feats, n, row_begin, row_end, dout, grads, dfeat, ws, ws_bytes, st);
+    return tc::trunk_backward_tc(net, feats, n, row_begin, row_end, dout, grads, dfeat, precision, ws, ws_bytes, st);
   }
   const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
   Layer L[COORDX_MAX_LAYERS + 1];

@@ -1,0 +1,69 @@
+// Shared pieces of the tcgen05 trunk kernels (forward: trunk_fwd_tc.cu, backward: trunk_bwd_tc.cu).
+#pragma once
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace coordx {
+namespace tc {
+
+constexpr int HD = 256;
+constexpr int TILE_M = 128;
+constexpr int KCHUNK = 64;                          // one SWIZZLE_128B row of 16-bit elements
+constexpr int NKC = HD / KCHUNK;                    // 4
+constexpr int MAX_O = 4;
+
+template <typename T>
+struct Pack;
+template <>
+struct Pack<__nv_bfloat16> {
+  using V2 = __nv_bfloat162;
+  static constexpr uint32_t kFmt = 1;
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <>
+struct Pack<__half> {
+  using V2 = __half2;
+  static constexpr uint32_t kFmt = 0;
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+template <typename T, int OP>
+__device__ __forceinline__ uint32_t fuse2(uint32_t x, uint32_t y) {
+  using V2 = typename Pack<T>::V2;
+  V2 a = *reinterpret_cast<V2*>(&x), b = *reinterpret_cast<V2*>(&y);
+  V2 r = OP == COORDX_FUSE_PROD ? __hmul2(a, b) : __hadd2(a, b);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+static inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- entry points of the two tcgen05 translation units (called from coordx_abi.cu)
+bool tc_supported(const coordx_net* net, int precision);
+size_t fwd_workspace_bytes(int64_t n_inner);
+int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
+                     int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+void profile_enable(bool on);
+int profile_last_ms(float* ms_host);
+
+size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1);
+int trunk_backward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
+                      const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws,
+                      size_t ws_bytes, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace coordx

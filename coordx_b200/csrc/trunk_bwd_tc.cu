@@ -19,12 +19,49 @@
 //   W_h  [128 n_out x 256 k_in] : B of G1 (K-major, N = n_out) and B of G2 (MN-major, N = k_in)
 //   H    [128 pts   x 256 k_in] : A of G1 (K-major)            and B of G3 (MN-major, N = k_in)
 //   dZ_h [128 pts   x 128 n_out]: A of G2 (K-major)            and A of G3 (MN-major, M = n_out)
-#pragma once
-#include "trunk_tc.cuh"
+#include "tc_common.cuh"
 
 namespace coordx {
 namespace tcb {
 using namespace tc;
+
+constexpr uint32_t W_CHUNK_BYTES = HD * 128;        // 32 KB: [256 rows x 128 B]
+constexpr uint32_t W_BYTES = NKC * W_CHUNK_BYTES;   // 128 KB
+constexpr uint32_t A_CHUNK_BYTES = TILE_M * 128;    // 16 KB
+constexpr uint32_t INNER_BYTES = NKC * A_CHUNK_BYTES;  // 64 KB per 128-row block
+
+template <typename T>
+__device__ __forceinline__ T to_T(float v);
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_T<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half to_T<__half>(float v) { return __float2half_rn(v); }
+
+// W fp32 [256(n), 256(k)] -> 4 K-chunks of [256 rows x 128 B] SWIZZLE_128B; epilogue constants
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ Wf,
+                    const float* __restrict__ bf, int O, int act, float S, uint8_t* __restrict__ w_img,
+                    void* __restrict__ /*unused*/) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;          // over 256*256
+  const int n = idx >> 8, k = idx & 255;
+  const uint32_t off = (k >> 6) * W_CHUNK_BYTES + ptx::sw128_offset(n, k & 63);
+  *reinterpret_cast<T*>(w_img + off) = to_T<T>(W[idx]);
+}
+
+// inner feature table fp32 [n, 256] -> per 128-row block: 4 K-chunks [128 rows x 128 B] SWIZZLE_128B
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_inner_kernel(const float* __restrict__ feat, int64_t n, uint8_t* __restrict__ img, int64_t n_padded) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;   // over n_padded*256
+  if (idx >= n_padded * HD) return;
+  const int64_t j = idx >> 8;
+  const int k = (int)(idx & 255);
+  const float v = j < n ? feat[idx] : 0.f;
+  const size_t off = (size_t)(j >> 7) * INNER_BYTES + (k >> 6) * A_CHUNK_BYTES + ptx::sw128_offset((uint32_t)(j & 127), k & 63);
+  *reinterpret_cast<T*>(img + off) = to_T<T>(v);
+}
+
 
 constexpr uint32_t CH = 16384;                    // one [128 rows x 128 B] SWIZZLE_128B chunk
 constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB)
@@ -585,7 +622,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   pl.nbB = (int)cdiv(pl.n_innerB, TILE_M);
   size_t off = 0;
   pl.w_img_off = off; off += align_up(W_BYTES, 1024);
-  pl.epi_off = off; off += align_up(sizeof(EpiConst), 1024);
+  pl.epi_off = off;
   pl.consts_off = off; off += align_up((1 + MAX_O) * HD * 4, 1024);
   pl.innerA_off = off; off += (size_t)pl.nbA * INNER_BYTES;
   pl.innerB_off = off; off += (size_t)pl.nbB * INNER_BYTES;
@@ -603,7 +640,6 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   if (!ws || ws_bytes < pl.total) return set_err(COORDX_ERR_WORKSPACE, "tcgen05 trunk backward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)pl.total);
   uint8_t* base = (uint8_t*)ws;
   uint8_t* w_img = base + pl.w_img_off;
-  EpiConst* epi = (EpiConst*)(base + pl.epi_off);
   float* consts = (float*)(base + pl.consts_off);
   uint8_t* innerA = base + pl.innerA_off;
   uint8_t* innerB = base + pl.innerB_off;
@@ -613,7 +649,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   const int64_t n_last = n[C - 1];
 
   prep_weights_kernel<T><<<HD * HD / 256, 256, 0, st>>>(net->layer_w[L], net->layer_b[L], net->layer_w[L + 1], net->layer_b[L + 1],
-                                                       O, net->act, S, w_img, epi);
+                                                       O, net->act, S, w_img, nullptr);
   CX_LAUNCH_CHECK();
   prep_bwd_consts_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], O, net->act, S, consts);
   CX_LAUNCH_CHECK();
@@ -666,4 +702,17 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
 }
 
 }  // namespace tcb
+}  // namespace coordx
+
+namespace coordx {
+namespace tc {
+size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1) { return tcb::plan_bwd(net, n, r0, r1).total; }
+int trunk_backward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
+                      const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  if (precision == COORDX_PREC_BF16)
+    return tcb::trunk_backward_tc_t<__nv_bfloat16>(net, feats, n, r0, r1, dout, grads, dfeat, ws, ws_bytes, st);
+  return tcb::trunk_backward_tc_t<__half>(net, feats, n, r0, r1, dout, grads, dfeat, ws, ws_bytes, st);
+}
+}  // namespace tc
 }  // namespace coordx

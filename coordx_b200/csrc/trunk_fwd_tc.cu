@@ -1,0 +1,460 @@
+// tcgen05 / TMEM fused fusion + trunk FORWARD, hidden = 256, one Hd x Hd trunk layer followed by
+// the Hd -> O layer (approx_layers = 2, num_hidden_layers = 3: SURVEY 8a configs 1, 2, 4, 5).
+//
+// Replaces SplitFCBlock.forward_fusion (modules.py:329-354).  The broadcast
+// h = hs[0] (+|*) hs[1] ... (modules.py:336-341) is generated 128 points at a time straight into the
+// UMMA operand layout in shared memory and never reaches HBM; the trunk BatchLinear
+// (modules.py:26-27) runs on the 5th-gen tensor cores with the fp32 accumulator in TMEM; bias,
+// sin(30 x) / ReLU (modules.py:39,172) and the final Hd -> O BatchLinear are applied in registers by
+// the epilogue warps.
+//
+// Why a CTA PAIR (cta_group::2).  A single-CTA M128 x N256 x K16 MMA reads 4 KB of A and 8 KB of B
+// from shared memory every 128 cycles (96 B/clk of the SM's 128 B/clk) - with the A-tile producer's
+// own traffic on top, the first version of this kernel was shared-memory bound at 53 % tensor-pipe
+// utilisation (profiles/r01a_fwd_trunk_full.txt).  Here two CTAs of a cluster issue ONE M256 x N256
+// MMA: each CTA supplies its own 128-point A tile and HALF of W (its 128 output features), so the
+// tensor core pulls 64 B/clk per SM, W takes 64 KB of shared memory instead of 128, and the freed
+// space is an 8-deep A ring.  The producers keep the inner-axis feature block in REGISTERS
+// (128 x 256 16-bit values = 128 registers per producer thread) for hundreds of tiles and only
+// write the fused A tile (32 B/clk): total 96 B/clk.
+//
+// Work decomposition: the LAST axis is the "inner" axis; a tile = 128 consecutive inner samples x one
+// combination `o` of the outer axes.  A-tile row p is  A[p, :] = rowvec(o) (+|*) inner[jb*128 + p, :]
+// with rowvec(o) = outer0[o] (C = 2) or outer0[i0] (+|*) outer1[i1] (C = 3).  Tiles are ordered
+// (jb major, o minor) and split contiguously over the clusters; inside a cluster the two CTAs take
+// alternate tiles, so both keep the same inner block most of the time.
+//
+// CTA = 16 warps (4 warpgroups, registers re-balanced with setmaxnreg), 1 CTA / SM:
+//   warps 0-3   epilogue group 0 (TMEM accumulator 0, even iterations), lane quadrant = warp % 4
+//   warps 4-7   epilogue group 1 (TMEM accumulator 1, odd iterations)
+//   warps 8-11  producers: inner block piece (registers) x rowvec piece (registers) -> A ring (smem, SW128)
+//   warp 12     TMEM alloc; in the LEADER CTA one lane issues tcgen05.mma.cta_group::2 for the pair
+//   warps 13-15 idle (complete the warpgroup that gives its registers away)
+// Shared memory: W half 64 KB (resident) | A ring 2 x 64 KB (whole tiles, 4 K-chunks of 64 each).
+#include "tc_common.cuh"
+
+namespace coordx {
+namespace tc {
+
+constexpr uint32_t CHUNK_BYTES = TILE_M * 128;      // 16 KB: [128 rows x 128 B]
+constexpr int A_STAGES = 2;                         // whole 128 x 256 tiles (4 chunks each)
+constexpr uint32_t SMEM_W = 0;                                      // 4 chunks: this CTA's 128 output features
+constexpr uint32_t TILE_BYTES = NKC * CHUNK_BYTES;                  // 64 KB
+constexpr uint32_t SMEM_A = SMEM_W + NKC * CHUNK_BYTES;             // A ring
+constexpr uint32_t SMEM_BAR = SMEM_A + A_STAGES * TILE_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
+constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to 1024-align the base by hand
+constexpr int NUM_THREADS = 16 * 32;
+constexpr int REGS_EPI = 128, REGS_PROD = 200, REGS_MMA = 56;       // 128 * (2*128 + 200 + 56) = 65536
+
+// epilogue constants (trunk bias pre-scaled, final layer): warp-uniform, compile-time offsets after
+// unrolling => FFMA operands straight from the constant bank
+struct EpiConst {
+  float bias[HD];            // sine: S*b ; relu: b
+  float wf[MAX_O][HD];       // final layer weight
+  float bf[MAX_O];
+};
+__constant__ EpiConst c_epi;
+
+__global__ void __launch_bounds__(256)
+prep_epi_kernel(const float* __restrict__ b, const float* __restrict__ Wf, const float* __restrict__ bf, int O, int act,
+                float S, EpiConst* __restrict__ epi) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;          // over MAX_O * 256
+  if (idx < HD) epi->bias[idx] = act == COORDX_ACT_SINE ? S * b[idx] : b[idx];
+  if (idx < MAX_O * HD) {
+    const int o = idx >> 8;
+    epi->wf[o][idx & 255] = o < O ? Wf[idx] : 0.f;
+  }
+  if (idx < MAX_O) epi->bf[idx] = idx < O ? bf[idx] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------
+struct FwdParams {
+  const float* W;           // trunk weight [256 (n_out), 256 (k_in)] fp32
+  const float* inner;       // inner-axis feature table [n_inner, 256] fp32
+  const float* outer0;      // [N0, 256] fp32
+  const float* outer1;      // [N1, 256] fp32 or nullptr
+  int64_t n_outer1;         // N1 (1 when outer1 == nullptr)
+  int64_t o_begin, o_end;   // slab of the flattened outer index
+  int64_t n_inner;
+  int nb;                   // inner blocks = ceil(n_inner / 128)
+  float* out;               // [(o_end - o_begin) * n_inner, O]
+  float S;
+};
+
+template <typename T, int OP, int ACT, int O>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+trunk_fwd_tc_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;     // same offset in both CTAs of the pair
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const uint32_t bar0 = smem_base + SMEM_BAR;
+  const uint32_t bar_full = bar0;              // [A_STAGES]  leader only: 8 producer warps (4 per CTA) have written the tile
+  const uint32_t bar_empty = bar0 + 64;        // [A_STAGES]  each CTA: the MMAs reading the tile have completed (multicast commit)
+  const uint32_t bar_tfull = bar0 + 128;       // [2]         each CTA: accumulator complete (multicast commit)
+  const uint32_t bar_tempty = bar0 + 144;      // [2]         leader only: 8 epilogue warps (4 per CTA) have drained the accumulator
+  const uint32_t tmem_slot = bar0 + 160;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_BAR + 160);
+
+  // tiles of this cluster; CTA `rank` takes tiles c_begin + 2*it + rank
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int64_t n_cl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+  const int64_t c_begin = total * cl / n_cl;
+  const int64_t c_end = total * (cl + 1) / n_cl;
+  const int n_iter = (int)((c_end - c_begin + 1) >> 1);
+
+  if (warp == 12) {
+    if (lane == 0) {
+      for (int s = 0; s < A_STAGES; ++s) {
+        ptx::mbar_init(bar_full + 8 * s, 8);
+        ptx::mbar_init(bar_empty + 8 * s, 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(bar_tfull + 8 * a, 1);
+        ptx::mbar_init(bar_tempty + 8 * a, 8);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc_2cta(tmem_slot, 512);
+    ptx::tmem_relinquish_2cta();
+  }
+  // ---- this CTA's half of W: fp32 [128 rows of n_out, 256] -> bf16/fp16, 4 K-chunks [128 x 128 B] SWIZZLE_128B
+  {
+    const float* Wh = p.W + (size_t)rank * 128 * HD;
+    for (int pc = threadIdx.x; pc < 128 * 32; pc += NUM_THREADS) {
+      const int n = pc >> 5, g = pc & 31;                  // row, 16-byte piece (8 elements) of the 256-wide row
+      const float4 a = *reinterpret_cast<const float4*>(Wh + n * HD + g * 8);
+      const float4 b = *reinterpret_cast<const float4*>(Wh + n * HD + g * 8 + 4);
+      uint4 w;
+      w.x = Pack<T>::pack(a.x, a.y);
+      w.y = Pack<T>::pack(a.z, a.w);
+      w.z = Pack<T>::pack(b.x, b.y);
+      w.w = Pack<T>::pack(b.z, b.w);
+      *reinterpret_cast<uint4*>(smem_gen + SMEM_W + (g >> 3) * CHUNK_BYTES + ptx::sw128_offset(n, (g & 7) * 8)) = w;
+    }
+    ptx::fence_proxy_async();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                                     // peer's barriers, W half and TMEM allocation are ready
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp >= 12) {
+    ptx::setmaxnreg_dec<REGS_MMA>();
+    if (warp == 12 && rank == 0 && lane == 0 && n_iter > 0) {
+      // ============================ MMA issuer (leader CTA, one thread) ============================
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 2 * TILE_M, HD);
+      for (int it = 0; it < n_iter; ++it) {
+        const uint32_t a = it & 1, use = it >> 1;          // accumulator == A stage == iteration parity
+        ptx::mbar_wait(bar_tempty + 8 * a, (use & 1) ^ 1);
+        ptx::mbar_wait(bar_full + 8 * a, use & 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * HD;
+        const uint32_t a_addr = smem_base + SMEM_A + a * TILE_BYTES;
+        const uint32_t b_addr = smem_base + SMEM_W;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+          ptx::mma_f16_ss_2cta(d_tmem, ptx::umma_desc_k_sw128(a_addr + off), ptx::umma_desc_k_sw128(b_addr + off), idesc, k != 0);
+        }
+        ptx::mma_commit_2cta(bar_empty + 8 * a, 3);
+        ptx::mma_commit_2cta(bar_tfull + 8 * a, 3);
+      }
+    }
+  } else if (warp >= 8) {
+    // ============================ producers ============================
+    ptx::setmaxnreg_inc<REGS_PROD>();
+    // thread (g = lane, rg = warp - 8) owns the 16-byte piece g (k = 8g .. 8g+7) of the 32 rows
+    // 32*rg .. 32*rg+31: its 8 rowvec values are 4 packed registers loaded straight from global
+    // memory (no broadcast through shared memory), and a warp's stores cover whole 128-byte lines.
+    const int g = lane, rg = warp - 8;
+    const uint32_t full_remote = ptx::mapa(bar_full, 0);
+    // byte offset of (row 32*rg, piece g) inside a tile stage, before the per-row swizzle
+    uint8_t* const a_base = smem_gen + SMEM_A + (uint32_t)(g >> 3) * CHUNK_BYTES + (uint32_t)rg * 4096u;
+    uint32_t in[32][4];                           // inner block rows x this piece, 16-bit pairs
+    int cur_jb = -1;
+    // tile -> (jb, o) without divisions in the loop: tiles advance by 2
+    int64_t t0 = c_begin + rank;
+    if (t0 >= c_end) t0 = c_end - 1;
+    int64_t t_next = c_begin + rank;
+    const int n_o32 = (int)n_o;
+    int jb = n_iter > 0 ? (int)(t0 / n_o) : 0;
+    int ol = n_iter > 0 ? (int)(t0 - (int64_t)jb * n_o) : 0;
+    auto load_rv = [&](int64_t o, float4& x0, float4& x1) {
+      int64_t i0 = o, i1 = 0;
+      if (p.outer1) { i0 = o / p.n_outer1; i1 = o - i0 * p.n_outer1; }
+      x0 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + 8 * g);
+      x1 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + 8 * g + 4);
+      if (p.outer1) {
+        const float4 y0 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + 8 * g);
+        const float4 y1 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + 8 * g + 4);
+        if (OP == COORDX_FUSE_PROD) {
+          x0.x *= y0.x; x0.y *= y0.y; x0.z *= y0.z; x0.w *= y0.w;
+          x1.x *= y1.x; x1.y *= y1.y; x1.z *= y1.z; x1.w *= y1.w;
+        } else {
+          x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+          x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+        }
+      }
+    };
+
+    for (int it = 0; it < n_iter; ++it) {
+      // rowvec piece of this tile (L2-resident table; the ~1 us of latency is slack: a tile needs ~600 of the
+      // producers' 2048 cycles) - not prefetched, the registers are needed for the inner block
+      uint32_t rv[4];
+      {
+        float4 x0, x1;
+        load_rv(p.o_begin + ol, x0, x1);
+        rv[0] = Pack<T>::pack(x0.x, x0.y);
+        rv[1] = Pack<T>::pack(x0.z, x0.w);
+        rv[2] = Pack<T>::pack(x1.x, x1.y);
+        rv[3] = Pack<T>::pack(x1.z, x1.w);
+      }
+      if (jb != cur_jb) {
+        // (rare: once per ~n_o tiles) reload the inner block piece.  Batches of 4 rows are chained through an
+        // opaque zero so that ptxas cannot hoist all 64 loads at once (it would spill the block to local memory).
+        uint32_t chain = 0;
+#pragma unroll
+        for (int r4 = 0; r4 < 32; r4 += 4) {
+          float4 v0[4], v1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t j = (int64_t)jb * TILE_M + rg * 32 + r4 + u;
+            v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v1[u] = v0[u];
+            if (j < p.n_inner) {
+              const float* src = p.inner + j * HD + 8 * g + chain;
+              v0[u] = *reinterpret_cast<const float4*>(src);
+              v1[u] = *reinterpret_cast<const float4*>(src + 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            in[r4 + u][0] = Pack<T>::pack(v0[u].x, v0[u].y);
+            in[r4 + u][1] = Pack<T>::pack(v0[u].z, v0[u].w);
+            in[r4 + u][2] = Pack<T>::pack(v1[u].x, v1[u].y);
+            in[r4 + u][3] = Pack<T>::pack(v1[u].z, v1[u].w);
+          }
+          asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(in[r4 + 3][3]));
+        }
+        cur_jb = jb;
+      }
+      // next tile of this CTA; past the end of the range (odd range, rank 1, last iteration) the previous
+      // tile is produced again and the epilogue discards it.
+      t_next += 2;
+      if (t_next < c_end) {
+        ol += 2;
+        while (ol >= n_o32) { ol -= n_o32; ++jb; }
+      }
+      const uint32_t st = it & 1, use = it >> 1;
+      ptx::mbar_wait(bar_empty + 8 * st, (use & 1) ^ 1);
+      uint8_t* dst = a_base + st * TILE_BYTES;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        uint4 w;
+        w.x = fuse2<T, OP>(in[r][0], rv[0]);
+        w.y = fuse2<T, OP>(in[r][1], rv[1]);
+        w.z = fuse2<T, OP>(in[r][2], rv[2]);
+        w.w = fuse2<T, OP>(in[r][3], rv[3]);
+        // row 32*rg + r: 8-row group (r >> 3) is 1024 bytes, row (r & 7) 128 bytes, piece XOR-swizzled with the row
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+      }
+      ptx::fence_proxy_async();             // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(full_remote + 8 * st);
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int e = warp >> 2;                      // accumulator / iteration parity
+    const int q = warp & 3;                       // TMEM lane quadrant
+    const int row = q * 32 + lane;
+    const uint32_t tempty_remote = ptx::mapa(bar_tempty + 8 * e, 0);
+    for (int it = e; it < n_iter; it += 2) {
+      const uint32_t use = it >> 1;
+      ptx::mbar_wait(bar_tfull + 8 * e, use & 1);
+      ptx::tc_fence_after();
+      const int64_t t = c_begin + 2 * (int64_t)it + rank;
+      const bool valid = t < c_end;
+      const int64_t jb = t / n_o;
+      const int64_t o_local = t - jb * n_o;
+      const uint32_t taddr = tmem_base + e * HD + ((uint32_t)(q * 32) << 16);
+      float acc[O];
+#pragma unroll
+      for (int oo = 0; oo < O; ++oo) acc[oo] = 0.f;
+      // TMEM -> registers double-buffered: the load of column batch cb+1 is in flight while
+      // batch cb goes through bias + sin/relu + the Hd -> O dot product.  Bias and final-layer
+      // weights are direct constant-bank operands of the FFMAs (an LDC per value is far slower).
+      uint32_t ra[32], rb[32];
+      auto consume = [&](const uint32_t (&r)[32], int cb) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k = cb * 32 + i;
+          const float z = __uint_as_float(r[i]);
+          float h;
+          if (ACT == COORDX_ACT_SINE)
+            h = __sinf(fmaf(z, p.S, c_epi.bias[k]));
+          else
+            h = fmaxf(z + c_epi.bias[k], 0.f);
+#pragma unroll
+          for (int oo = 0; oo < O; ++oo) acc[oo] = fmaf(h, c_epi.wf[oo][k], acc[oo]);
+        }
+      };
+      ptx::tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll
+      for (int cb = 0; cb < HD / 32; cb += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, rb);
+        consume(ra, cb);
+        ptx::tmem_ld_wait();
+        if (cb + 2 < HD / 32) ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
+        consume(rb, cb + 1);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_remote);
+      const int64_t j = jb * TILE_M + row;
+      if (valid && j < p.n_inner) {
+        float* dst = p.out + (o_local * p.n_inner + j) * O;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo) dst[oo] = acc[oo] + c_epi.bf[oo];
+      }
+    }
+  }
+
+  // both CTAs are done with each other's shared memory / TMEM before anything is torn down
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 12) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+struct FwdPlan {
+  size_t epi_off, total;
+  int nb;
+};
+
+static FwdPlan plan_fwd(int64_t n_inner) {
+  FwdPlan pl{};
+  pl.nb = (int)cdiv(n_inner, TILE_M);
+  size_t off = 0;
+  pl.epi_off = off; off += align_up(sizeof(EpiConst), 1024);
+  pl.total = off;
+  return pl;
+}
+
+// optional device timing of the main kernel alone (bench.py roofline)
+static bool g_profile = false;
+static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+void profile_enable(bool on) { g_profile = on; }
+// milliseconds of the last profiled trunk kernel (synchronises on its end event)
+int profile_last_ms(float* ms_host) {
+  if (!ms_host || !g_prof_ev[0]) return set_err(COORDX_ERR_ARG, "no profiled launch%s");
+  CX_CUDA(cudaEventSynchronize(g_prof_ev[1]));
+  CX_CUDA(cudaEventElapsedTime(ms_host, g_prof_ev[0], g_prof_ev[1]));
+  return 0;
+}
+size_t fwd_workspace_bytes(int64_t n_inner) { return plan_fwd(n_inner).total; }
+
+template <typename T, int OP, int ACT, int O>
+static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
+  auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
+    attr_done = true;
+  }
+  if (g_profile) {
+    if (!g_prof_ev[0]) {
+      CX_CUDA(cudaEventCreate(&g_prof_ev[0]));
+      CX_CUDA(cudaEventCreate(&g_prof_ev[1]));
+    }
+    CX_CUDA(cudaEventRecord(g_prof_ev[0], st));
+  }
+  kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);      // cluster shape (2,1,1) is a compile-time attribute of the kernel
+  CX_LAUNCH_CHECK();
+  if (g_profile) CX_CUDA(cudaEventRecord(g_prof_ev[1], st));
+  return 0;
+}
+
+template <typename T, int OP, int ACT>
+static int launch_fwd_o(const FwdParams& fp, int O, int grid, cudaStream_t st) {
+  switch (O) {
+    case 1: return launch_fwd_inst<T, OP, ACT, 1>(fp, grid, st);
+    case 2: return launch_fwd_inst<T, OP, ACT, 2>(fp, grid, st);
+    case 3: return launch_fwd_inst<T, OP, ACT, 3>(fp, grid, st);
+    case 4: return launch_fwd_inst<T, OP, ACT, 4>(fp, grid, st);
+  }
+  return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk: out width %s%lld > 4", "", O);
+}
+
+template <typename T>
+static int launch_fwd_t(const FwdParams& fp, int op, int act, int O, int grid, cudaStream_t st) {
+  if (op == COORDX_FUSE_PROD)
+    return act == COORDX_ACT_SINE ? launch_fwd_o<T, COORDX_FUSE_PROD, COORDX_ACT_SINE>(fp, O, grid, st)
+                                  : launch_fwd_o<T, COORDX_FUSE_PROD, COORDX_ACT_RELU>(fp, O, grid, st);
+  return act == COORDX_ACT_SINE ? launch_fwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_SINE>(fp, O, grid, st)
+                                : launch_fwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU>(fp, O, grid, st);
+}
+
+// feats: C tables [n_c, 256] fp32.  The last axis is the inner axis; axes 0..C-2 are outer.
+int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
+                     int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int C = net->n_branches;
+  const int L = net->n_pre;                       // trunk = layers L (Hd x Hd) and L+1 (Hd -> O)
+  const int O = net->layer_out[L + 1];
+  const int64_t n_inner = n[C - 1];
+  const FwdPlan pl = plan_fwd(n_inner);
+  if (ws_bytes < pl.total || ws == nullptr) return set_err(COORDX_ERR_WORKSPACE, "tcgen05 trunk: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)pl.total);
+  EpiConst* epi = (EpiConst*)((uint8_t*)ws + pl.epi_off);
+  const float S = 30.f * net->act_scale;
+
+  prep_epi_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], net->layer_b[L + 1], O, net->act, S, epi);
+  CX_LAUNCH_CHECK();
+  CX_CUDA(cudaMemcpyToSymbolAsync(c_epi, epi, sizeof(EpiConst), 0, cudaMemcpyDeviceToDevice, st));
+
+  FwdParams fp{};
+  fp.W = net->layer_w[L];
+  fp.inner = feats[C - 1];
+  fp.outer0 = feats[0];
+  fp.outer1 = C == 3 ? feats[1] : nullptr;
+  fp.n_outer1 = C == 3 ? n[1] : 1;
+  fp.o_begin = row_begin * fp.n_outer1;
+  fp.o_end = row_end * fp.n_outer1;
+  fp.n_inner = n_inner;
+  fp.nb = pl.nb;
+  fp.out = out;
+  fp.S = S;
+  const int64_t total = (int64_t)pl.nb * (fp.o_end - fp.o_begin);
+  if (total <= 0) return 0;
+  const int grid = 2 * (int)min((int64_t)(num_sms() / 2), cdiv(total, 2));
+  if (precision == COORDX_PREC_BF16) return launch_fwd_t<__nv_bfloat16>(fp, net->fusion_op, net->act, O, grid, st);
+  return launch_fwd_t<__half>(fp, net->fusion_op, net->act, O, grid, st);
+}
+
+bool tc_supported(const coordx_net* net, int precision) {
+  if (precision != COORDX_PREC_BF16 && precision != COORDX_PREC_FP16) return false;
+  const int C = net->n_branches, L = net->n_pre;
+  if (C < 2 || C > 3) return false;
+  if (net->hidden != HD || net->fuse_width != HD) return false;
+  if (net->n_layers - net->n_pre != 2) return false;
+  if (net->layer_in[L] != HD || net->layer_out[L] != HD || net->layer_in[L + 1] != HD) return false;
+  if (net->layer_out[L + 1] < 1 || net->layer_out[L + 1] > MAX_O) return false;
+  if (net->fusion_before_act || net->has_code) return false;
+  if (net->act != COORDX_ACT_SINE && net->act != COORDX_ACT_RELU) return false;
+  return true;
+}
+
+}  // namespace tc
+}  // namespace coordx

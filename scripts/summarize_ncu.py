@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+  python scripts/summarize_ncu.py launches gpurun_out/launches_fwd.csv  > profiles/r01_fwd_launches.txt
+  python scripts/summarize_ncu.py full     gpurun_out/prof_fwd.ncu-rep  > profiles/r01_fwd_trunk_full.txt
+"""
+import csv
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEEP = re.compile(
+    r'^(gpu__time_duration\.sum|dram__bytes_(read|write)\.sum|sm__cycles_(elapsed|active)\.avg|'
+    r'sm__pipe_tensor_cycles_active_realtime\.avg\.pct_of_peak_sustained_elapsed|'
+    r'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime\.avg|'
+    r'sm__inst_executed_pipe_(xu|fma|alu|fmaheavy|fmalite|lsu|uniform)\.avg\.pct_of_peak_sustained_active|'
+    r'sm__inst_executed_pipe_xu_realtime\.avg\.pct_of_peak_sustained_elapsed|'
+    r'l1tex__data_pipe_(lsu|tc)_wavefronts_mem_shared\.sum\.pct_of_peak_sustained_elapsed|'
+    r'l1tex__data_pipe_(lsu|tc)_wavefronts_mem_shared\.sum|'
+    r'l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum|'
+    r'launch__(registers_per_thread|shared_mem_per_block_dynamic|grid_size|block_size|cluster.*)|'
+    r'smsp__warp_issue_stalled_.*_per_warp_active\.pct|smsp__issue_active\.avg\.pct_of_peak_sustained_active|'
+    r'sm__throughput\.avg\.pct_of_peak_sustained_elapsed|gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed|'
+    r'sm__warps_active\.avg\.pct_of_peak_sustained_active|smsp__inst_executed\.sum|'
+    r'lts__t_bytes\.sum|gpc__cycles_elapsed\.avg\.per_second)$')
+
+
+def launches(path):
+    rows = list(csv.reader(open(path, errors='replace')))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
+    hdr = rows[start]
+    iname, ival = hdr.index('Kernel Name'), hdr.index('Metric Value')
+    agg, total, n = OrderedDict(), 0.0, 0
+    for r in rows[start + 1:]:
+        if len(r) <= ival:
+            continue
+        v = float(r[ival].replace(',', ''))
+        a = agg.setdefault(r[iname], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        total += v
+        n += 1
+    print(f'# {path}: {n} launches, {total / 1e3:.1f} us of device time (ncu: cold-cache, serialised; compare SHARES)')
+    print(f'{"count":>6} {"total_us":>11} {"share":>7} {"avg_us":>10}  kernel')
+    for name, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f'{c:6d} {v / 1e3:11.1f} {100 * v / total:6.1f}% {v / c / 1e3:10.1f}  {name[:110]}')
+
+
+def full(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f'# {path}: ncu --set full --clock-control none; selected metrics per captured launch')
+    for r in rows[2:]:
+        print(f'\n== {r[hdr.index("Kernel Name")]}  grid {r[hdr.index("Grid Size")]} block {r[hdr.index("Block Size")]}')
+        for h, u, v in zip(hdr, units, r):
+            if KEEP.match(h):
+                print(f'  {h:95s} {v:>16s} {u}')
+
+
+if __name__ == '__main__':
+    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
