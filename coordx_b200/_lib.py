@@ -11,7 +11,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libcoordx_b200.so')
+LIB_PATH = os.environ.get('COORDX_B200_LIB') or os.path.join(HERE, 'libcoordx_b200.so')   # override: tuning builds only
 
 MAX_BRANCHES = 4
 MAX_LAYERS = 12
@@ -70,6 +70,7 @@ SIGNATURES = {
     'coordx_launch_count': (C.c_ulonglong, []),
     'coordx_profile_enable': (C.c_int, [C.c_int]),
     'coordx_profile_last_ms': (C.c_int, [C.POINTER(C.c_float)]),
+    'coordx_profile_set_trace': (C.c_int, [C.c_void_p]),
     'coordx_trunk_tc_supported': (C.c_int, [C.POINTER(Net), C.c_int]),
     'coordx_branch_workspace_bytes': (C.c_size_t, [C.POINTER(Net), C.c_int, C.c_int64, C.c_int]),
     'coordx_branch_forward': (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -177,6 +177,13 @@ int coordx_profile_enable(int on) {
   return 0;
 }
 
+// device buffer of 4 x 96 x 4 int64 that CTA 0 of the forward trunk kernel fills with SM-clock stamps of its
+// pipeline events (roles: MMA issuer, epilogue 0/1, producer warp 8); nullptr switches it off
+int coordx_profile_set_trace(void* dev_buf) {
+  tc::profile_set_trace(dev_buf);
+  return 0;
+}
+
 // milliseconds of the last profiled trunk kernel (synchronises on its end event)
 int coordx_profile_last_ms(float* ms_host) {
   return tc::profile_last_ms(ms_host);

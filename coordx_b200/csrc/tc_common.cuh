@@ -58,6 +58,7 @@ size_t fwd_workspace_bytes(int64_t n_inner);
 int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
                      int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 void profile_enable(bool on);
+void profile_set_trace(void* dev_buf);
 int profile_last_ms(float* ms_host);
 
 size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1);

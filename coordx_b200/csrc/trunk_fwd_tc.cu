@@ -15,7 +15,7 @@
 // MMA: each CTA supplies its own 128-point A tile and HALF of W (its 128 output features), so the
 // tensor core pulls 64 B/clk per SM, W takes 64 KB of shared memory instead of 128, and the freed
 // space is an 8-deep A ring.  The producers keep the inner-axis feature block in REGISTERS
-// (128 x 256 16-bit values = 128 registers per producer thread) for hundreds of tiles and only
+// (128 x 256 16-bit values = 64 registers per producer thread) for hundreds of tiles and only
 // write the fused A tile (32 B/clk): total 96 B/clk.
 //
 // Work decomposition: the LAST axis is the "inner" axis; a tile = 128 consecutive inner samples x one
@@ -24,13 +24,15 @@
 // (jb major, o minor) and split contiguously over the clusters; inside a cluster the two CTAs take
 // alternate tiles, so both keep the same inner block most of the time.
 //
-// CTA = 16 warps (4 warpgroups, registers re-balanced with setmaxnreg), 1 CTA / SM:
-//   warps 0-3   epilogue group 0 (TMEM accumulator 0, even iterations), lane quadrant = warp % 4
-//   warps 4-7   epilogue group 1 (TMEM accumulator 1, odd iterations)
-//   warps 8-11  producers: inner block piece (registers) x rowvec piece (registers) -> A ring (smem, SW128)
-//   warp 12     TMEM alloc; in the LEADER CTA one lane issues tcgen05.mma.cta_group::2 for the pair
-//   warps 13-15 idle (complete the warpgroup that gives its registers away)
+// CTA = 20 warps (5 warpgroups, registers re-balanced with setmaxnreg), 1 CTA / SM:
+//   warps 0-3   epilogue group 0: columns   0..127 of every accumulator, lane quadrant = warp % 4
+//   warps 4-7   epilogue group 1: columns 128..255 of every accumulator
+//   warps 8-15  producers: inner block piece (registers) x rowvec piece (registers) -> A ring (smem, SW128)
+//   warp 16     TMEM alloc; in the LEADER CTA one lane issues tcgen05.mma.cta_group::2 for the pair
+//   warps 17-19 idle (complete the warpgroup that gives its registers away)
 // Shared memory: W half 64 KB (resident) | A ring 2 x 64 KB (whole tiles, 4 K-chunks of 64 each).
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -41,11 +43,18 @@ constexpr int A_STAGES = 2;                         // whole 128 x 256 tiles (4 
 constexpr uint32_t SMEM_W = 0;                                      // 4 chunks: this CTA's 128 output features
 constexpr uint32_t TILE_BYTES = NKC * CHUNK_BYTES;                  // 64 KB
 constexpr uint32_t SMEM_A = SMEM_W + NKC * CHUNK_BYTES;             // A ring
-constexpr uint32_t SMEM_BAR = SMEM_A + A_STAGES * TILE_BYTES;
+constexpr uint32_t SMEM_PB = SMEM_A + A_STAGES * TILE_BYTES;        // float pb[256]: S b / 2pi + 6144 (polynomial sine path)
+constexpr uint32_t SMEM_PWF = SMEM_PB + HD * 4;                     // __half2 pwf[MAX_O][128]: final-layer weights as fp16 pairs
+constexpr uint32_t SMEM_XCH = SMEM_PWF + MAX_O * (HD / 2) * 4;          // float xch[2][MAX_O][128]
+constexpr uint32_t SMEM_BAR = SMEM_XCH + 2 * MAX_O * TILE_M * 4;
 constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to 1024-align the base by hand
-constexpr int NUM_THREADS = 16 * 32;
-constexpr int REGS_EPI = 128, REGS_PROD = 200, REGS_MMA = 56;       // 128 * (2*128 + 200 + 56) = 65536
+constexpr int NUM_THREADS = 20 * 32;
+#ifndef COORDX_FWD_MUFU_COLS
+#define COORDX_FWD_MUFU_COLS 32
+#endif
+// launch: 640 threads x 96 registers; then 256 x 96 (epilogue, unchanged) + 256 x 128 (producers) + 128 x 32 (MMA warpgroup) = 640 x 96
+constexpr int REGS_PROD = 128, REGS_MMA = 32;
 
 // epilogue constants (trunk bias pre-scaled, final layer): warp-uniform, compile-time offsets after
 // unrolling => FFMA operands straight from the constant bank
@@ -80,9 +89,43 @@ struct FwdParams {
   int nb;                   // inner blocks = ceil(n_inner / 128)
   float* out;               // [(o_end - o_begin) * n_inner, O]
   float S;
+  long long* trace;         // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
 };
+constexpr int TRACE_ITERS = 96;
 
-template <typename T, int OP, int ACT, int O>
+// sin(2 pi t) for the "polynomial" share of the epilogue's columns (SINE only).  The MUFU unit evaluates
+// 16 sin/clk/SM - exactly one 128 x 256 tile per 2048 clk, the tcgen05 time of the same tile - so an
+// all-MUFU epilogue can never run ahead of the tensor core.  NM of every 32 columns use MUFU.SIN, the rest:
+//   u  = z * S/2pi + (S b/2pi + 6144)     fp32 FFMA; 6144 = 1.5 * 2^12 makes ulp(u) = 2^-11, so the low 11
+//                                         mantissa bits of u are round(frac(t) * 2^11): free range reduction
+//   x  = 0x3C00 | (bits 9..0)             fp16 in [1, 2) encoding the position inside the half period
+//   |sin| = cos(pi (x - 1.5))             even polynomial of degree 6 in fp16x2 (HFMA2: two columns per op)
+//   sign  = bit 10                        XORed into the fp16 sign bits
+//   acc  += sin * wf                      FHFMA (fp16 x fp16 + fp32)
+// Error of this path: 6.5e-4 rms / 2.2e-3 max per activation (oracle-checked in tests), below the
+// ~1.3e-3 rad the bf16 operands already put on the sine's argument; output parity stays well inside 2e-3.
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {      // c + a.lo * b.lo
+  float r;
+  asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, al, bl, %3;\n\t}"
+      : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t a, uint32_t b, float c) {      // c + a.hi * b.hi
+  float r;
+  asm("{\n\t.reg .f16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, ah, bh, %3;\n\t}"
+      : "=f"(r) : "r"(a), "r"(b), "f"(c));
+  return r;
+}
+constexpr float POLY_MAGIC = 6144.f;
+constexpr float POLY_C0 = 0.99999325f, POLY_C1 = -4.93393467f, POLY_C2 = 4.0412481f, POLY_C3 = -1.22203176f;
+
+__device__ __forceinline__ void trace_stamp(const FwdParams& p, int role, int it, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_ITERS) p.trace[(role * TRACE_ITERS + it) * 4 + slot] = clock64();
+}
+
+template <typename T, int OP, int ACT, int O, int NM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 trunk_fwd_tc_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -92,10 +135,10 @@ trunk_fwd_tc_kernel(const FwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const uint32_t bar0 = smem_base + SMEM_BAR;
-  const uint32_t bar_full = bar0;              // [A_STAGES]  leader only: 8 producer warps (4 per CTA) have written the tile
+  const uint32_t bar_full = bar0;              // [A_STAGES]  leader only: 16 producer warps (8 per CTA) have written the tile
   const uint32_t bar_empty = bar0 + 64;        // [A_STAGES]  each CTA: the MMAs reading the tile have completed (multicast commit)
   const uint32_t bar_tfull = bar0 + 128;       // [2]         each CTA: accumulator complete (multicast commit)
-  const uint32_t bar_tempty = bar0 + 144;      // [2]         leader only: 8 epilogue warps (4 per CTA) have drained the accumulator
+  const uint32_t bar_tempty = bar0 + 144;      // [2]         leader only: 16 epilogue warps (8 per CTA) have drained the accumulator
   const uint32_t tmem_slot = bar0 + 160;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_BAR + 160);
 
@@ -107,15 +150,15 @@ trunk_fwd_tc_kernel(const FwdParams p) {
   const int64_t c_end = total * (cl + 1) / n_cl;
   const int n_iter = (int)((c_end - c_begin + 1) >> 1);
 
-  if (warp == 12) {
+  if (warp == 16) {
     if (lane == 0) {
       for (int s = 0; s < A_STAGES; ++s) {
-        ptx::mbar_init(bar_full + 8 * s, 8);
+        ptx::mbar_init(bar_full + 8 * s, 16);
         ptx::mbar_init(bar_empty + 8 * s, 1);
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(bar_tfull + 8 * a, 1);
-        ptx::mbar_init(bar_tempty + 8 * a, 8);
+        ptx::mbar_init(bar_tempty + 8 * a, 16);
       }
       ptx::fence_mbar_init();
     }
@@ -125,19 +168,31 @@ trunk_fwd_tc_kernel(const FwdParams p) {
   }
   // ---- this CTA's half of W: fp32 [128 rows of n_out, 256] -> bf16/fp16, 4 K-chunks [128 x 128 B] SWIZZLE_128B
   {
+    // SINE: the activation scale S = 30 * act_scale is folded into the 16-bit weights (W' = S W), so the
+    // accumulator already holds S z and the epilogue adds the pre-scaled bias with one packed FADD2
+    const float ws = ACT == COORDX_ACT_SINE ? p.S : 1.f;
     const float* Wh = p.W + (size_t)rank * 128 * HD;
     for (int pc = threadIdx.x; pc < 128 * 32; pc += NUM_THREADS) {
       const int n = pc >> 5, g = pc & 31;                  // row, 16-byte piece (8 elements) of the 256-wide row
       const float4 a = *reinterpret_cast<const float4*>(Wh + n * HD + g * 8);
       const float4 b = *reinterpret_cast<const float4*>(Wh + n * HD + g * 8 + 4);
       uint4 w;
-      w.x = Pack<T>::pack(a.x, a.y);
-      w.y = Pack<T>::pack(a.z, a.w);
-      w.z = Pack<T>::pack(b.x, b.y);
-      w.w = Pack<T>::pack(b.z, b.w);
+      w.x = Pack<T>::pack(ws * a.x, ws * a.y);
+      w.y = Pack<T>::pack(ws * a.z, ws * a.w);
+      w.z = Pack<T>::pack(ws * b.x, ws * b.y);
+      w.w = Pack<T>::pack(ws * b.z, ws * b.w);
       *reinterpret_cast<uint4*>(smem_gen + SMEM_W + (g >> 3) * CHUNK_BYTES + ptx::sw128_offset(n, (g & 7) * 8)) = w;
     }
     ptx::fence_proxy_async();
+  }
+  if (NM < 32) {
+    float* pb = reinterpret_cast<float*>(smem_gen + SMEM_PB);
+    __half2* pwf = reinterpret_cast<__half2*>(smem_gen + SMEM_PWF);
+    for (int i = threadIdx.x; i < HD; i += NUM_THREADS) pb[i] = c_epi.bias[i] * 0.15915494309189535f + POLY_MAGIC;
+    for (int i = threadIdx.x; i < MAX_O * (HD / 2); i += NUM_THREADS) {
+      const int o = i / (HD / 2), k2 = i % (HD / 2);
+      pwf[i] = __floats2half2_rn(c_epi.wf[o][2 * k2], c_epi.wf[o][2 * k2 + 1]);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -145,15 +200,18 @@ trunk_fwd_tc_kernel(const FwdParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp >= 12) {
+  if (warp >= 16) {
     ptx::setmaxnreg_dec<REGS_MMA>();
-    if (warp == 12 && rank == 0 && lane == 0 && n_iter > 0) {
+    if (warp == 16 && rank == 0 && lane == 0 && n_iter > 0) {
       // ============================ MMA issuer (leader CTA, one thread) ============================
       constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 2 * TILE_M, HD);
       for (int it = 0; it < n_iter; ++it) {
         const uint32_t a = it & 1, use = it >> 1;          // accumulator == A stage == iteration parity
+        trace_stamp(p, 0, it, 0);
         ptx::mbar_wait(bar_tempty + 8 * a, (use & 1) ^ 1);
+        trace_stamp(p, 0, it, 1);
         ptx::mbar_wait(bar_full + 8 * a, use & 1);
+        trace_stamp(p, 0, it, 2);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * HD;
         const uint32_t a_addr = smem_base + SMEM_A + a * TILE_BYTES;
@@ -164,20 +222,21 @@ trunk_fwd_tc_kernel(const FwdParams p) {
           ptx::mma_f16_ss_2cta(d_tmem, ptx::umma_desc_k_sw128(a_addr + off), ptx::umma_desc_k_sw128(b_addr + off), idesc, k != 0);
         }
         ptx::mma_commit_2cta(bar_empty + 8 * a, 3);
+        trace_stamp(p, 0, it, 3);
         ptx::mma_commit_2cta(bar_tfull + 8 * a, 3);
       }
     }
   } else if (warp >= 8) {
     // ============================ producers ============================
     ptx::setmaxnreg_inc<REGS_PROD>();
-    // thread (g = lane, rg = warp - 8) owns the 16-byte piece g (k = 8g .. 8g+7) of the 32 rows
-    // 32*rg .. 32*rg+31: its 8 rowvec values are 4 packed registers loaded straight from global
+    // thread (g = lane, rg = warp - 8) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows
+    // 16*rg .. 16*rg+15: its 8 rowvec values are 4 packed registers loaded straight from global
     // memory (no broadcast through shared memory), and a warp's stores cover whole 128-byte lines.
     const int g = lane, rg = warp - 8;
     const uint32_t full_remote = ptx::mapa(bar_full, 0);
-    // byte offset of (row 32*rg, piece g) inside a tile stage, before the per-row swizzle
-    uint8_t* const a_base = smem_gen + SMEM_A + (uint32_t)(g >> 3) * CHUNK_BYTES + (uint32_t)rg * 4096u;
-    uint32_t in[32][4];                           // inner block rows x this piece, 16-bit pairs
+    // byte offset of (row 16*rg, piece g) inside a tile stage, before the per-row swizzle
+    uint8_t* const a_base = smem_gen + SMEM_A + (uint32_t)(g >> 3) * CHUNK_BYTES + (uint32_t)rg * 2048u;
+    uint32_t in[16][4];                           // inner block rows x this piece, 16-bit pairs
     int cur_jb = -1;
     // tile -> (jb, o) without divisions in the loop: tiles advance by 2
     int64_t t0 = c_begin + rank;
@@ -221,11 +280,11 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         // opaque zero so that ptxas cannot hoist all 64 loads at once (it would spill the block to local memory).
         uint32_t chain = 0;
 #pragma unroll
-        for (int r4 = 0; r4 < 32; r4 += 4) {
+        for (int r4 = 0; r4 < 16; r4 += 4) {
           float4 v0[4], v1[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int64_t j = (int64_t)jb * TILE_M + rg * 32 + r4 + u;
+            const int64_t j = (int64_t)jb * TILE_M + rg * 16 + r4 + u;
             v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             v1[u] = v0[u];
             if (j < p.n_inner) {
@@ -253,85 +312,161 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         while (ol >= n_o32) { ol -= n_o32; ++jb; }
       }
       const uint32_t st = it & 1, use = it >> 1;
+      if (threadIdx.x == 8 * 32) trace_stamp(p, 3, it, 0);
       ptx::mbar_wait(bar_empty + 8 * st, (use & 1) ^ 1);
+      if (threadIdx.x == 8 * 32) trace_stamp(p, 3, it, 1);
       uint8_t* dst = a_base + st * TILE_BYTES;
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
+      for (int r = 0; r < 16; ++r) {
         uint4 w;
         w.x = fuse2<T, OP>(in[r][0], rv[0]);
         w.y = fuse2<T, OP>(in[r][1], rv[1]);
         w.z = fuse2<T, OP>(in[r][2], rv[2]);
         w.w = fuse2<T, OP>(in[r][3], rv[3]);
-        // row 32*rg + r: 8-row group (r >> 3) is 1024 bytes, row (r & 7) 128 bytes, piece XOR-swizzled with the row
+        // row 16*rg + r: 8-row group (r >> 3) is 1024 bytes, row (r & 7) 128 bytes, piece XOR-swizzled with the row
         *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
       }
       ptx::fence_proxy_async();             // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(full_remote + 8 * st);
+      if (threadIdx.x == 8 * 32) trace_stamp(p, 3, it, 2);
     }
   } else {
     // ============================ epilogue ============================
-    const int e = warp >> 2;                      // accumulator / iteration parity
+    // all 8 warps work on EVERY tile: group e = warp >> 2 takes columns [128 e, 128 e + 128) of the
+    // accumulator, so one tile is drained in half the time and the accumulator goes back to the tensor
+    // core before the other one is complete (two groups that each owned an accumulator ran in phase
+    // and left the MMA idle ~40 % of the time: profiles/r01b_fwd_timeline.txt)
+    const int e = warp >> 2;                      // column half
     const int q = warp & 3;                       // TMEM lane quadrant
     const int row = q * 32 + lane;
-    const uint32_t tempty_remote = ptx::mapa(bar_tempty + 8 * e, 0);
-    for (int it = e; it < n_iter; it += 2) {
-      const uint32_t use = it >> 1;
-      ptx::mbar_wait(bar_tfull + 8 * e, use & 1);
+    float* xch = reinterpret_cast<float*>(smem_gen + SMEM_XCH);     // [2][MAX_O][128] partial outputs of group 1
+    // (the column half is a compile-time constant inside the body so that bias / final-layer weights stay
+    //  direct constant-bank operands)
+    auto run = [&](auto EC) {
+    constexpr int E = decltype(EC)::value;
+    for (int it = 0; it < n_iter; ++it) {
+      const uint32_t a = it & 1, use = it >> 1;
+      const uint32_t tempty_remote = ptx::mapa(bar_tempty + 8 * a, 0);
+      if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 0);
+      ptx::mbar_wait(bar_tfull + 8 * a, use & 1);
+      if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 1);
       ptx::tc_fence_after();
       const int64_t t = c_begin + 2 * (int64_t)it + rank;
       const bool valid = t < c_end;
       const int64_t jb = t / n_o;
       const int64_t o_local = t - jb * n_o;
-      const uint32_t taddr = tmem_base + e * HD + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + a * HD + E * (HD / 2) + ((uint32_t)(q * 32) << 16);
+      // acc2: packed pair (even-column sum, odd-column sum) fed by FFMA2; acc: the polynomial path's FHFMAs
+      uint64_t acc2[O];
       float acc[O];
 #pragma unroll
-      for (int oo = 0; oo < O; ++oo) acc[oo] = 0.f;
+      for (int oo = 0; oo < O; ++oo) { acc2[oo] = 0ull; acc[oo] = 0.f; }
       // TMEM -> registers double-buffered: the load of column batch cb+1 is in flight while
       // batch cb goes through bias + sin/relu + the Hd -> O dot product.  Bias and final-layer
       // weights are direct constant-bank operands of the FFMAs (an LDC per value is far slower).
       uint32_t ra[32], rb[32];
-      auto consume = [&](const uint32_t (&r)[32], int cb) {
+      auto consume = [&](const uint32_t (&r)[32], int cbl) {
+        const int cb = E * 4 + cbl;               // 32-column batch inside the 256-wide accumulator
+        constexpr int NMU = ACT == COORDX_ACT_SINE ? NM : 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < NMU; i += 2) {
+          // MUFU path, two columns per packed fp32x2 instruction: FADD2 (bias pair from uniform registers),
+          // 2 x (FMUL.RZ + MUFU.SIN), FFMA2 into the packed accumulator = 3.25 issue slots per activation
           const int k = cb * 32 + i;
-          const float z = __uint_as_float(r[i]);
-          float h;
-          if (ACT == COORDX_ACT_SINE)
-            h = __sinf(fmaf(z, p.S, c_epi.bias[k]));
-          else
-            h = fmaxf(z + c_epi.bias[k], 0.f);
+          const uint64_t zz = ptx::pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+          float t0, t1;
+          ptx::unpack_f32x2(ptx::add_f32x2(zz, ptx::pack_f32x2(c_epi.bias[k], c_epi.bias[k + 1])), t0, t1);
+          float h0, h1;
+          if (ACT == COORDX_ACT_SINE) {
+            h0 = __sinf(t0);
+            h1 = __sinf(t1);
+          } else {
+            h0 = fmaxf(t0, 0.f);
+            h1 = fmaxf(t1, 0.f);
+          }
+          const uint64_t hh = ptx::pack_f32x2(h0, h1);
 #pragma unroll
-          for (int oo = 0; oo < O; ++oo) acc[oo] = fmaf(h, c_epi.wf[oo][k], acc[oo]);
+          for (int oo = 0; oo < O; ++oo)
+            acc2[oo] = ptx::fma_f32x2(hh, ptx::pack_f32x2(c_epi.wf[oo][k], c_epi.wf[oo][k + 1]), acc2[oo]);
+        }
+        if (NMU < 32) {
+          // polynomial path, two columns per fp16x2 operation
+          const float Sp = 0.15915494309189535f;      // the accumulator holds S z (S is folded into the weights)
+          const __half2 c0 = __float2half2_rn(POLY_C0), c1 = __float2half2_rn(POLY_C1), c2 = __float2half2_rn(POLY_C2),
+                        c3 = __float2half2_rn(POLY_C3), mh = __float2half2_rn(-1.5f);
+#pragma unroll
+          for (int i = NMU; i < 32; i += 4) {
+            const int k = cb * 32 + i;
+            const float4 b4 = *reinterpret_cast<const float4*>(smem_gen + SMEM_PB + k * 4);            // warp-uniform: broadcast
+            uint2 w2[O];
+#pragma unroll
+            for (int oo = 0; oo < O; ++oo) w2[oo] = *reinterpret_cast<const uint2*>(smem_gen + SMEM_PWF + (oo * (HD / 2) + k / 2) * 4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float u0 = fmaf(__uint_as_float(r[i + 2 * j]), Sp, bb[2 * j]);
+              const float u1 = fmaf(__uint_as_float(r[i + 2 * j + 1]), Sp, bb[2 * j + 1]);
+              const uint32_t w = __byte_perm(__float_as_uint(u0), __float_as_uint(u1), 0x5410);   // {u1.lo16, u0.lo16}
+              const __half2 v = __hadd2(u32_as_h2((w & 0x03FF03FFu) | 0x3C003C00u), mh);
+              const __half2 v2 = __hmul2(v, v);
+              __half2 q = __hfma2(c3, v2, c2);
+              q = __hfma2(q, v2, c1);
+              q = __hfma2(q, v2, c0);
+              const uint32_t hs = h2_as_u32(q) ^ ((w << 5) & 0x80008000u);
+#pragma unroll
+              for (int oo = 0; oo < O; ++oo) {
+                const uint32_t wf2 = j == 0 ? w2[oo].x : w2[oo].y;
+                acc[oo] = fhfma_lo(hs, wf2, acc[oo]);
+                acc[oo] = fhfma_hi(hs, wf2, acc[oo]);
+              }
+            }
+          }
         }
       };
       ptx::tmem_ld_32x32b_x32(taddr, ra);
 #pragma unroll
-      for (int cb = 0; cb < HD / 32; cb += 2) {
+      for (int cb = 0; cb < HD / 64; cb += 2) {
         ptx::tmem_ld_wait();
         ptx::tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, rb);
         consume(ra, cb);
         ptx::tmem_ld_wait();
-        if (cb + 2 < HD / 32) ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
+        if (cb + 2 < HD / 64) ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
         consume(rb, cb + 1);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(tempty_remote);
+      if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 2);
+      // the two column halves of a row meet in shared memory: group 1 deposits, group 0 adds and stores
+      float* xb = xch + (it & 1) * (MAX_O * TILE_M);
+#pragma unroll
+      for (int oo = 0; oo < O; ++oo) {
+        float lo, hi;
+        ptx::unpack_f32x2(acc2[oo], lo, hi);
+        acc[oo] += lo + hi;
+      }
+      if (E == 1) {
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo) xb[oo * TILE_M + row] = acc[oo];
+      }
+      ptx::named_bar_sync(2 + q, 64);          // only the two warps that share this lane quadrant (rows) meet
       const int64_t j = jb * TILE_M + row;
-      if (valid && j < p.n_inner) {
+      if (E == 0 && valid && j < p.n_inner) {
         float* dst = p.out + (o_local * p.n_inner + j) * O;
 #pragma unroll
-        for (int oo = 0; oo < O; ++oo) dst[oo] = acc[oo] + c_epi.bf[oo];
+        for (int oo = 0; oo < O; ++oo) dst[oo] = acc[oo] + xb[oo * TILE_M + row] + c_epi.bf[oo];
       }
     }
+    };
+    if (e == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
   }
 
   // both CTAs are done with each other's shared memory / TMEM before anything is torn down
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
-  if (warp == 12) {
+  if (warp == 16) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2cta(tmem_base, 512);
   }
@@ -357,7 +492,9 @@ static FwdPlan plan_fwd(int64_t n_inner) {
 // optional device timing of the main kernel alone (bench.py roofline)
 static bool g_profile = false;
 static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
+static long long* g_trace = nullptr;
 void profile_enable(bool on) { g_profile = on; }
+void profile_set_trace(void* dev_buf) { g_trace = (long long*)dev_buf; }
 // milliseconds of the last profiled trunk kernel (synchronises on its end event)
 int profile_last_ms(float* ms_host) {
   if (!ms_host || !g_prof_ev[0]) return set_err(COORDX_ERR_ARG, "no profiled launch%s");
@@ -367,9 +504,14 @@ int profile_last_ms(float* ms_host) {
 }
 size_t fwd_workspace_bytes(int64_t n_inner) { return plan_fwd(n_inner).total; }
 
+// columns per 32 that take MUFU.SIN; the polynomial share is only used with bf16 operands, whose own
+// rounding already dominates the error (fp16 operands keep the exact path)
+template <typename T> struct MufuCols { static constexpr int value = 32; };
+template <> struct MufuCols<__nv_bfloat16> { static constexpr int value = COORDX_FWD_MUFU_COLS; };
+
 template <typename T, int OP, int ACT, int O>
 static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
-  auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O>;
+  auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, (ACT == COORDX_ACT_SINE ? MufuCols<T>::value : 32)>;
   static bool attr_done = false;
   if (!attr_done) {
     CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
@@ -436,6 +578,7 @@ int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int
   fp.nb = pl.nb;
   fp.out = out;
   fp.S = S;
+  fp.trace = g_trace;
   const int64_t total = (int64_t)pl.nb * (fp.o_end - fp.o_begin);
   if (total <= 0) return 0;
   const int grid = 2 * (int)min((int64_t)(num_sms() / 2), cdiv(total, 2));

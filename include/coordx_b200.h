@@ -92,6 +92,8 @@ const char* coordx_last_error(void);
 unsigned long long coordx_launch_count(void);
 int coordx_profile_enable(int on);
 int coordx_profile_last_ms(float* ms_host);
+/* optional pipeline timeline of the forward trunk kernel: device buffer of 4*96*4 int64 (see profiles/), NULL = off */
+int coordx_profile_set_trace(void* dev_buf);
 /* 1 if the tcgen05 trunk kernels cover this architecture at `precision`. */
 int coordx_trunk_tc_supported(const coordx_net* net, int precision);
 
