@@ -146,6 +146,7 @@ def main():
     config = {'workload': f'train_img.py synthetic {H}x{W} image per GPU, sine split MLP, fusion=prod, hidden 256, '
                           f'{args.precision} trunk (BASELINE configs[1])',
               'grid_per_gpu': [H, W], 'hidden': HIDDEN, 'fusion': 'prod', 'l2': 'flushed between timed iterations (256 MiB write)',
+              'launch': 'value: CUDA-graph replay of forward_split_channel x2 + forward_split_fusion; e2e: one coordx_infer_grid_host call',
               'sharding': 'axis-0 slab per rank, no data-path collective'}
 
     if args.impl == 'reference':
@@ -225,18 +226,20 @@ def main():
     time.sleep(0.3)
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
+    # One step = the reference's two-stage --speed_test sequence (train_img.py:125-135).  It is replayed from a
+    # CUDA graph (coordx_b200.runtime.CapturedGrid): ~0.4 ms of GPU work per step is otherwise stretched ~25 % by
+    # Python gaps between the launches.  The eager (no graph) figure is reported next to it.
+    from coordx_b200 import runtime as RT
     kernel_ms = []
     with torch.no_grad():
         launches0 = lib.coordx_launch_count()
+        fwd(x, y)
+        launches_per_step = lib.coordx_launch_count() - launches0
+        cap = RT.CapturedGrid(model, [x, y])
+        total_ms = timed(cap.replay, args.steps, warmup)
+        eager_ms = timed(lambda: fwd(x, y), args.steps, warmup)
+        # dominant kernel alone: a few extra eager launches, each read back from its own event pair
         lib.coordx_profile_enable(1)
-
-        def step_dev():
-            fwd(x, y)
-            v = ctypes.c_float(0)
-            # (reading the event later would be cheaper; the sync happens after e1 is recorded)
-        total_ms = timed(step_dev, args.steps, warmup)
-        launches_per_step = (lib.coordx_launch_count() - launches0) // (args.steps + warmup)
-        # dominant kernel alone: a few extra launches, each read back from its own event pair
         for _ in range(5):
             flush.zero_()
             fwd(x, y)
@@ -245,13 +248,14 @@ def main():
             kernel_ms.append(v.value)
         lib.coordx_profile_enable(0)
 
-        # ---- e2e: pinned host in, result to pinned host out, public python API ----------------
+        # ---- e2e: pinned host coordinates in, [P,1] result to pinned host memory, ONE C-ABI call
+        # (coordx_infer_grid_host: H2D copies, branch MLPs, trunk, D2H copy all inside the timed region)
         def step_e2e():
-            xd = x_host.to(dev, non_blocking=True)
-            yd = y_host.to(dev, non_blocking=True)
-            o = fwd(xd, yd)
-            out_host.copy_(o.reshape(-1, 1), non_blocking=True)
+            RT.infer_grid_host(model, [x_host, y_host], out_host)
         e2e_ms = timed(step_e2e, args.steps, warmup)
+        # the result that came back over PCIe is the same as the graph's
+        torch.cuda.synchronize()
+        e2e_check = float((out_host.reshape(-1) - cap.replay().reshape(-1).cpu()).abs().max())
 
     ms_per_step = total_ms / args.steps
     value = P * world / (ms_per_step * 1e-3)
@@ -264,7 +268,8 @@ def main():
     roof = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops'], 'unit': 'TFLOP/s',
             'frac': achieved / pk['bf16_tflops'], 'traffic': None, 'peak_kind': pk_kind + ' burst (kernel timed alone)',
             'kernel': 'trunk_fwd_tc_kernel', 'kernel_ms': k_ms, 'flop_per_launch': F_kernel,
-            'step_frac_of_sustained': F / (ms_per_step * 1e-3) / 1e12 / pk.get('bf16_tflops_sustained', pk['bf16_tflops'])}
+            'step_frac_of_sustained': F / (ms_per_step * 1e-3) / 1e12 / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
+            'eager_ms_per_step': eager_ms / args.steps, 'e2e_vs_graph_max_abs_diff': e2e_check}
 
     # ---- training iteration (fwd + MSE + bwd + Adam), extra keys -------------------------------
     train = None
@@ -297,8 +302,8 @@ def main():
                  'e2e_value': args.train_steps / (tr_e2e_ms * 1e-3),
                  'tflops_algorithmic': 3 * F / (tr_ms / args.train_steps * 1e-3) / 1e12,
                  'frac_of_sustained_peak': 3 * F / (tr_ms / args.train_steps * 1e-3) / 1e12 / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
-                 'note': 'forward on tcgen05 (bf16), backward on the FP32 FFMA kernels (round 1); global grid = this '
-                         'rank\'s slab, grads all-reduced over NCCL when N>1'}
+                 'note': 'eager step through the reference-shaped API: model(dict) -> MSE -> loss.backward() -> Adam; forward and '
+                         'backward trunk on tcgen05 (bf16); global grid = this rank\'s slab, grads all-reduced over NCCL when N>1'}
 
     clocks = sampler.finish()
 

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_f32.cuh"
+#include "branch_fused.cuh"
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -211,6 +212,7 @@ int coordx_branch_forward(const coordx_net* net, int branch, const float* coords
   if (branch < 0 || branch >= net->n_branches) return set_err(COORDX_ERR_ARG, "branch out of range%s (%lld)", "", branch);
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (bf::supported(net)) return bf::launch(net, branch, branch + 1, &coords, &n, &feat, st);
   Layer L[COORDX_MAX_LAYERS + 1];
   const int nl = branch_layers(net, branch, nullptr, L);
   Arena ar(ws, ws_bytes);
@@ -427,8 +429,36 @@ int coordx_infer_grid_host(const coordx_net* net, const float* const* coords_hos
   }
   const float* feats[COORDX_MAX_BRANCHES];
   for (int c = 0; c < C; ++c) feats[c] = dfeat[c];
-  CX_TRY(coordx_trunk_forward(net, feats, n, 0, n[0], dout, precision, scratch, sws, stream));
-  CX_CUDA(cudaMemcpyAsync(out_host, dout, (size_t)P * ow * 4, cudaMemcpyDeviceToHost, st));
+  // The [P, O] result is the only large transfer (16 MB for 2048^2: ~0.4 ms of PCIe, as long as the whole
+  // computation).  The grid is evaluated in axis-0 slabs and each slab's device->host copy runs on a second
+  // stream while the next slab is computed.
+  static cudaStream_t copy_stream = nullptr;
+  static cudaEvent_t ev_slab[8], ev_done = nullptr;
+  if (!copy_stream) {
+    CX_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CX_CUDA(cudaEventCreateWithFlags(&ev_slab[i], cudaEventDisableTiming));
+    CX_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+  }
+  const int64_t inner = P / n[0];
+  const size_t out_bytes = (size_t)P * ow * 4;
+  int slabs = out_bytes >= ((size_t)4 << 20) ? 4 : 1;
+  if (slabs > n[0]) slabs = (int)n[0];
+  for (int i = 0; i < slabs; ++i) {
+    const int64_t ra = n[0] * i / slabs, rb = n[0] * (i + 1) / slabs;
+    float* dslab = dout + ra * inner * ow;
+    CX_TRY(coordx_trunk_forward(net, feats, n, ra, rb, dslab, precision, scratch, sws, stream));
+    if (slabs == 1) {
+      CX_CUDA(cudaMemcpyAsync(out_host, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+      CX_CUDA(cudaEventRecord(ev_slab[i], st));
+      CX_CUDA(cudaStreamWaitEvent(copy_stream, ev_slab[i], 0));
+      CX_CUDA(cudaMemcpyAsync(out_host + ra * inner * ow, dslab, (size_t)(rb - ra) * inner * ow * 4, cudaMemcpyDeviceToHost, copy_stream));
+    }
+  }
+  if (slabs > 1) {                                  // the caller synchronises on `stream` only
+    CX_CUDA(cudaEventRecord(ev_done, copy_stream));
+    CX_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
+  }
   return 0;
 }
 

@@ -153,8 +153,77 @@ def _grads_for(block, params):
     return g, bufs
 
 
+_WS = {}
+
+
 def _workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    """Grow-only scratch buffer per (device, stream): kernels that use it are ordered on that stream,
+    so consecutive calls may share it (the C library never keeps pointers into it across calls)."""
+    nbytes = max(int(nbytes), 256)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes or torch.cuda.is_current_stream_capturing():
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if not torch.cuda.is_current_stream_capturing():
+            _WS[key] = ws
+    return ws
+
+
+def _net_desc(block, params, n_tables=None):
+    """struct coordx_net for `block`, rebuilt only when a parameter tensor moved."""
+    if not all(p.dtype == torch.float32 and p.is_contiguous() for p in params):
+        return _NetDesc(block, params, n_tables)          # _as_f32c makes copies: nothing to cache
+    key = tuple(p.data_ptr() for p in params)
+    cache = block.__dict__.setdefault('_desc_cache', {})
+    d = cache.get(n_tables)
+    if d is None or d.key != key:
+        d = _NetDesc(block, params, n_tables)
+        d.key = key
+        cache[n_tables] = d
+    return d
+
+
+def _branch_forward(block, branch, coords, params):
+    lib = _lib.load()
+    x = _as_f32c(coords)
+    if not x.is_cuda:
+        raise _lib.CoordxError('coordx_b200: the grid path needs CUDA tensors (no CPU fallback)')
+    n = x.shape[0]
+    desc = _net_desc(block, params)
+    feat = torch.empty(n, block.fuse_width, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 0)
+        ws = _workspace(ws_bytes, x.device)
+        _lib.check(lib.coordx_branch_forward(desc.net, branch, x.data_ptr(), n, feat.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream_ptr()), 'coordx_branch_forward')
+    return feat, x
+
+
+def _fusion_forward(block, precision, feats, params):
+    lib = _lib.load()
+    feats = [_as_f32c(t) for t in feats]
+    dev = feats[0].device
+    if not dev.type == 'cuda':
+        raise _lib.CoordxError('coordx_b200: the grid path needs CUDA tensors (no CPU fallback)')
+    ns = [f.shape[0] for f in feats]
+    desc = _net_desc(block, params, len(feats))
+    prec = block.resolve_precision(desc.net, precision)
+    P = 1
+    for v in ns:
+        P *= v
+    out = torch.empty(P, block.out_width, dtype=torch.float32, device=dev)
+    n_arr = _lib.i64_array(ns)
+    f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
+    with torch.cuda.device(dev):
+        ws_bytes = lib.coordx_trunk_workspace_bytes(desc.net, n_arr, 0, ns[0], prec, 0)
+        ws = _workspace(ws_bytes, dev)
+        _lib.check(lib.coordx_trunk_forward(desc.net, f_arr, n_arr, 0, ns[0], out.data_ptr(), prec, ws.data_ptr(),
+                                            ws.numel(), _stream_ptr()), 'coordx_trunk_forward')
+    return out, feats, prec
+
+
+def _needs_grad(tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
 
 
 class _BranchFn(torch.autograd.Function):
@@ -162,18 +231,7 @@ class _BranchFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, block, branch, coords, *params):
-        lib = _lib.load()
-        x = _as_f32c(coords)
-        if not x.is_cuda:
-            raise _lib.CoordxError('coordx_b200: the grid path needs CUDA tensors (no CPU fallback)')
-        n = x.shape[0]
-        desc = _NetDesc(block, params)
-        feat = torch.empty(n, block.fuse_width, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 0)
-            ws = _workspace(ws_bytes, x.device)
-            _lib.check(lib.coordx_branch_forward(desc.net, branch, x.data_ptr(), n, feat.data_ptr(), ws.data_ptr(),
-                                                 ws.numel(), _stream_ptr()), 'coordx_branch_forward')
+        feat, x = _branch_forward(block, branch, coords, params)
         ctx.block, ctx.branch = block, branch
         ctx.save_for_backward(x, *params)
         return feat
@@ -205,24 +263,8 @@ class _FusionFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, block, precision, nfeat, *tensors):
-        lib = _lib.load()
-        feats = [_as_f32c(t) for t in tensors[:nfeat]]
         params = tensors[nfeat:]
-        dev = feats[0].device
-        if not dev.type == 'cuda':
-            raise _lib.CoordxError('coordx_b200: the grid path needs CUDA tensors (no CPU fallback)')
-        ns = [f.shape[0] for f in feats]
-        desc = _NetDesc(block, params, n_tables=nfeat)
-        prec = block.resolve_precision(desc.net, precision)
-        P = int(np.prod(ns))
-        out = torch.empty(P, block.out_width, dtype=torch.float32, device=dev)
-        n_arr = _lib.i64_array(ns)
-        f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
-        with torch.cuda.device(dev):
-            ws_bytes = lib.coordx_trunk_workspace_bytes(desc.net, n_arr, 0, ns[0], prec, 0)
-            ws = _workspace(ws_bytes, dev)
-            _lib.check(lib.coordx_trunk_forward(desc.net, f_arr, n_arr, 0, ns[0], out.data_ptr(), prec, ws.data_ptr(),
-                                                ws.numel(), _stream_ptr()), 'coordx_trunk_forward')
+        out, feats, prec = _fusion_forward(block, precision, tensors[:nfeat], params)
         ctx.block, ctx.prec, ctx.nfeat = block, prec, nfeat
         ctx.save_for_backward(*feats, *params)
         return out
@@ -409,7 +451,12 @@ class SplitFCBlock(nn.Module):
     def forward_channel(self, coord, channel_id, pos_codes=None):
         """modules.py:311-327.  coord [..., f_c] -> [..., F]"""
         lead = coord.shape[:-1]
-        h = _BranchFn.apply(self, channel_id, coord.reshape(-1, coord.shape[-1]), *self.abi_params())
+        params = self.abi_params()
+        x2 = coord.reshape(-1, coord.shape[-1])
+        if _needs_grad([coord, *params]):
+            h = _BranchFn.apply(self, channel_id, x2, *params)
+        else:
+            h = _branch_forward(self, channel_id, x2, params)[0]        # inference: no autograd bookkeeping
         h = h.reshape(*lead, h.shape[-1])
         if pos_codes is not None and self.approx_layers > 0:
             h = h + pos_codes
@@ -425,7 +472,11 @@ class SplitFCBlock(nn.Module):
         feats = [hs[i].reshape(-1, hs[i].shape[-1]) for i in order]
         if len(feats) < 2 or len(feats) > _lib.MAX_BRANCHES:
             return self._fusion_eager(hs)
-        out = _FusionFn.apply(self, precision, len(feats), *feats, *self.abi_params())
+        params = self.abi_params()
+        if _needs_grad([*feats, *params]):
+            out = _FusionFn.apply(self, precision, len(feats), *feats, *params)
+        else:
+            out = _fusion_forward(self, precision, feats, params)[0]
         return out.reshape(*out_lead, out.shape[-1])
 
     def _fusion_eager(self, hs):
