@@ -3,22 +3,31 @@
 // in training.py:137-138, without ever materialising the [P, Hd] activations.
 //
 // Per 128-point tile (same tiling as the forward: rowvec(o) (+|*) 128 rows of the inner axis):
-//   G1  Z   = H  W_h^T            recompute the pre-activation            (tensor core)
-//   E1  dZ  = (dout Wf) * act'(Z) -> bf16 tile in smem; column sums give db and dWf
+//   G1  Z^T = W_h H^T             recompute the pre-activation, TRANSPOSED: lanes = output feature n
+//   E1  dZ^T = (dout Wf) * act'(Z^T) -> 16-bit tile in smem; db[n], dWf[n] are per-thread running sums
 //   G3  dW_h += dZ^T H            accumulated in TMEM over ALL tiles of the CTA, flushed once
-//   G2  dH  = dZ W_h              (two 128-column pieces)                  (tensor core)
+//   G2  dH  = dZ W_h              (two 128-column pieces)
 //   E2  d rowvec(o) = sum_p dH[p,:] * inner[p,:]   (prod)  |  sum_p dH[p,:]   (sum)
 // dW alone is 256x256 fp32 = all 512 TMEM columns, so a CTA owns ONE HALF h of the trunk's
-// output features (n_out in [128h, 128h+128)): Z_h is 128 columns, dW_h 256, a dH piece 128.
+// output features (n_out in [128h, 128h+128)): Z^T_h is 128 columns, dW_h 256, a dH piece 128.
 // The partial dH of the two halves add up linearly in the d-rowvec atomics.  The gradient of
 // the INNER axis' features needs the other reduction direction (over tiles, not inside a
 // tile); it is obtained by running the same kernel a second time with the two axes' roles
 // swapped and G3 switched off (DO_DW = false).
 //
+// Why Z is computed transposed.  With points on the TMEM lanes (first version) every bias / final-weight
+// gradient was a cross-lane reduction: 62 shuffles per 32 columns per warp, and E1 (4 warps, sin AND cos per
+// element) was the longest stage of a fully serialised G1 -> E1 -> G3/G2 -> E2 chain (12.2 k clk per tile for
+// 3.1 k clk of tensor work, profiles/r01a_train_launches.txt).  With the output feature on the lane, bias'[n],
+// wfs[n], db[n] and dWf[n] are per-thread registers, E1 runs on 8 warps (two per lane quadrant, 64 points
+// each) and hands the dZ tile to the tensor core in two 64-point chunks so G3 starts half an E1 early.
+//
 // The same shared-memory tiles serve as K-major and as MN-major UMMA operands:
-//   W_h  [128 n_out x 256 k_in] : B of G1 (K-major, N = n_out) and B of G2 (MN-major, N = k_in)
-//   H    [128 pts   x 256 k_in] : A of G1 (K-major)            and B of G3 (MN-major, N = k_in)
-//   dZ_h [128 pts   x 128 n_out]: A of G2 (K-major)            and A of G3 (MN-major, M = n_out)
+//   W_h   [128 n_out x 256 k_in] : A of G1 (K-major, M = n_out)    and B of G2 (MN-major, N = k_in)
+//   H     [128 pts   x 256 k_in] : B of G1 (K-major, N = pts)      and B of G3 (MN-major, N = k_in)
+//   dZ^T_h[128 n_out x 128 pts ] : A of G3 (K-major, M = n_out)    and A of G2 (MN-major, M = pts)
+//
+// CTA = 17 warps: 0-7 E1 (quadrant = warp % 4, point half = warp / 4) | 8-11 E2 | 12-15 producers | 16 MMA issuer.
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -68,10 +77,11 @@ constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB)
 constexpr uint32_t SM_H = 4 * CH;                 // 4 chunks (64 KB)
 constexpr uint32_t SM_DZ = 8 * CH;                // 2 chunks (32 KB)
 constexpr uint32_t SM_INNER = 10 * CH;            // 4 chunks (64 KB)
-constexpr uint32_t SM_CONST = 14 * CH;            // float bias'[128], wfs[MAX_O][128]
-constexpr uint32_t SM_BAR = SM_CONST + (1 + MAX_O) * 128 * 4;
-constexpr uint32_t SM_TOTAL_B = SM_BAR + 192;     // 232128 bytes <= 227 KB
-constexpr int BWD_THREADS = 13 * 32;
+constexpr uint32_t SM_BAR = 14 * CH;
+constexpr uint32_t SM_DOUT = SM_BAR + 256;        // float dout[128 points][MAX_O] of the current tile (staged by the producers)
+constexpr uint32_t SM_TOTAL_B = SM_DOUT + TILE_M * MAX_O * 4;     // 231680 bytes <= 227 KB
+constexpr int BWD_THREADS = 17 * 32;
+constexpr int W_E2 = 8, W_PROD = 12, W_MMA = 16;  // first warp of each role
 
 struct BwdParams {
   const uint8_t* w_img;      // full W image of the forward prep: 4 K-chunks of [256 rows x 128 B]
@@ -145,16 +155,15 @@ trunk_bwd_tc_kernel(const BwdParams p) {
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem_gen = smem_raw;
-  float* s_bias = reinterpret_cast<float*>(smem_gen + SM_CONST);
-  float* s_wfs = s_bias + 128;                     // [MAX_O][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_base + SM_BAR;
   const uint32_t bar_full = bar0;                  // [4] H chunk written        (128 producers)
   const uint32_t bar_empty = bar0 + 32;            // [4] H chunk no longer read (tcgen05.commit)
   const uint32_t bar_zfull = bar0 + 64;
-  const uint32_t bar_zempty = bar0 + 72;           // E1 has read Z              (128)
-  const uint32_t bar_dzfull = bar0 + 80;           // E1 has written dZ          (128)
+  const uint32_t bar_zempty = bar0 + 72;           // E1 has read Z^T            (256)
+  const uint32_t bar_dzfull = bar0 + 152;          // [2] E1 has written the 64-point chunk of dZ^T (128 each)
+  const uint32_t bar_dsfull = bar0 + 168;          // producers have staged dout of the tile (128)
   const uint32_t bar_dzempty = bar0 + 88;          // G2/G3 have read dZ         (commit)
   const uint32_t bar_dhfull = bar0 + 96;
   const uint32_t bar_dhempty = bar0 + 104;         // E2 has read the dH piece   (128)
@@ -173,15 +182,17 @@ trunk_bwd_tc_kernel(const BwdParams p) {
   const int64_t t_end = total * (cta + 1) / n_cta;
   const int my_tiles = (int)(t_end - t_begin);
 
-  if (warp == 12) {
+  if (warp == W_MMA) {
     if (lane == 0) {
       for (int c = 0; c < 4; ++c) {
         ptx::mbar_init(bar_full + 8 * c, 128);
         ptx::mbar_init(bar_empty + 8 * c, 1);
       }
       ptx::mbar_init(bar_zfull, 1);
-      ptx::mbar_init(bar_zempty, 128);
+      ptx::mbar_init(bar_zempty, 256);
       ptx::mbar_init(bar_dzfull, 128);
+      ptx::mbar_init(bar_dzfull + 8, 128);
+      ptx::mbar_init(bar_dsfull, 128);
       ptx::mbar_init(bar_dzempty, 1);
       ptx::mbar_init(bar_dhfull, 1);
       ptx::mbar_init(bar_dhempty, 128);
@@ -195,17 +206,13 @@ trunk_bwd_tc_kernel(const BwdParams p) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < (1 + MAX_O) * 128; i += BWD_THREADS) {
-    const int arr = i >> 7, n = i & 127;           // arr 0 = bias', 1.. = wfs[arr-1]
-    s_bias[i] = arr == 0 ? p.consts[h * 128 + n] : p.consts[HD + (arr - 1) * HD + h * 128 + n];
-  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   const uint32_t tZ = tmem_base, tDH = tmem_base + 128, tDW = tmem_base + 256;
 
-  if (warp == 12) {
+  if (warp == W_MMA) {
     // ============================ MMA issuer ============================
     if (lane == 0 && my_tiles > 0) {
       ptx::mbar_arrive_expect_tx(bar_w, 4 * CH);
@@ -213,15 +220,15 @@ trunk_bwd_tc_kernel(const BwdParams p) {
         ptx::bulk_g2s(smem_base + SM_W + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, bar_w);
       ptx::mbar_wait(bar_w, 0);
       constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 0);
-      constexpr uint32_t id_g2 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 1);
-      constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 1, 1);
+      constexpr uint32_t id_g2 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 1);   // A = dZ (M = pts) MN-major, B = W_h (N = k_in) MN-major
+      constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (M = n_out) K-major, B = H (N = k_in) MN-major
       uint32_t dh_uses = 0;
       auto issue_g2 = [&](int piece) {
         ptx::mbar_wait(bar_dhempty, (dh_uses & 1) ^ 1);
         ptx::tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {           // K = 128 n_out of this half, 16 per step
-          const uint64_t a = ptx::umma_desc_k_sw128(smem_base + SM_DZ + (ks >> 2) * CH + (ks & 3) * 32);
+        for (int ks = 0; ks < 8; ++ks) {           // K = 128 n_out of this half = 16 rows of the dZ^T tile per step
+          const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_DZ + ks * 2048, CH);
           const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_W + piece * 2 * CH + ks * 2048, CH);
           ptx::mma_f16_ss(tDH, a, b, id_g2, ks != 0);
         }
@@ -237,7 +244,7 @@ trunk_bwd_tc_kernel(const BwdParams p) {
           issue_g2(1);
           ptx::mma_commit(bar_dzempty);
         }
-        // ---- G1(t): Z_h = H W_h^T
+        // ---- G1(t): Z^T_h = W_h H^T   (A = W_h, M = n_out; B = H, N = points)
         ptx::mbar_wait(bar_zempty, (t & 1) ^ 1);
         ptx::tc_fence_after();
 #pragma unroll 1
@@ -246,8 +253,8 @@ trunk_bwd_tc_kernel(const BwdParams p) {
           ptx::tc_fence_after();
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(tZ, ptx::umma_desc_k_sw128(smem_base + SM_H + kc * CH + k * 32),
-                            ptx::umma_desc_k_sw128(smem_base + SM_W + kc * CH + k * 32), id_g1, (kc | k) != 0);
+            ptx::mma_f16_ss(tZ, ptx::umma_desc_k_sw128(smem_base + SM_W + kc * CH + k * 32),
+                            ptx::umma_desc_k_sw128(smem_base + SM_H + kc * CH + k * 32), id_g1, (kc | k) != 0);
           if (!DO_DW) ptx::mma_commit(bar_empty + 8 * kc);
         }
         ptx::mma_commit(bar_zfull);
@@ -255,20 +262,26 @@ trunk_bwd_tc_kernel(const BwdParams p) {
           issue_g2(1);
           ptx::mma_commit(bar_dzempty);
         }
-        ptx::mbar_wait(bar_dzfull, t & 1);
-        ptx::tc_fence_after();
-        // ---- G3(t): dW_h[:, 64c..] += dZ_h^T H[:, 64c..]   (K = 128 points, 16 per step)
+        // ---- G3(t): dW_h += dZ^T_h H   (K = 128 points, 16 per step; starts on the first 64-point chunk of dZ^T)
         if (DO_DW) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
+            ptx::mbar_wait(bar_dzfull + 8 * c, t & 1);
+            ptx::tc_fence_after();
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_DZ + ks * 2048, CH);
-              const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_H + c * CH + ks * 2048, CH);
-              ptx::mma_f16_ss(tDW + c * 64, a, b, id_g3, (t | ks) != 0);
+            for (int k = 0; k < 4; ++k) {
+              const int ks = c * 4 + k;
+              const uint64_t a = ptx::umma_desc_k_sw128(smem_base + SM_DZ + c * CH + k * 32);
+              const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_H + ks * 2048, CH);
+              ptx::mma_f16_ss(tDW, a, b, id_g3, (t | ks) != 0);
             }
-            ptx::mma_commit(bar_empty + 8 * c);
           }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) ptx::mma_commit(bar_empty + 8 * c);
+        } else {
+          ptx::mbar_wait(bar_dzfull, t & 1);
+          ptx::mbar_wait(bar_dzfull + 8, t & 1);
+          ptx::tc_fence_after();
         }
         // ---- G2a(t)
         issue_g2(0);
@@ -278,9 +291,9 @@ trunk_bwd_tc_kernel(const BwdParams p) {
       ptx::mma_commit(bar_dwfull);
     }
     __syncwarp();
-  } else if (warp >= 8) {
+  } else if (warp >= W_PROD) {
     // ============================ producers: H tile ============================
-    const int ptid = threadIdx.x - 8 * 32;
+    const int ptid = threadIdx.x - W_PROD * 32;
     const int g8 = ptid & 7, r0 = ptid >> 3;
     const uint32_t piece_off = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((g8 ^ (r0 & 7)) << 4);
     uint32_t inner_phase = 0;
@@ -313,6 +326,15 @@ trunk_bwd_tc_kernel(const BwdParams p) {
           rv[kc][2] = Pack<T>::pack(x1.x, x1.y);
           rv[kc][3] = Pack<T>::pack(x1.z, x1.w);
         }
+      }
+      // dout of this thread's point (row ptid of the tile): loaded now, staged for E1 after the H chunks
+      float dreg[O];
+      {
+        const int64_t j = jb * TILE_M + ptid;
+        const int64_t o_local = tt - jb * n_o;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo)
+          dreg[oo] = j < p.n_inner ? __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo) : 0.f;
       }
       if (jb != cur_jb) {
         ptx::named_bar_sync(1, 128);
@@ -350,73 +372,89 @@ trunk_bwd_tc_kernel(const BwdParams p) {
         ptx::fence_proxy_async();
         ptx::mbar_arrive(bar_full + 8 * kc);
       }
+      // E1(t-1) has read its dout (it arrives on zempty after its last read); G1(t) runs meanwhile
+      ptx::mbar_wait(bar_zempty, (t & 1) ^ 1);
+      {
+        float* ds = reinterpret_cast<float*>(smem_gen + SM_DOUT) + ptid * O;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo) ds[oo] = dreg[oo];
+      }
+      ptx::mbar_arrive(bar_dsfull);
     }
-  } else if (warp < 4) {
-    // ============================ E1: Z_h -> dZ_h (+ db, dWf column sums) ============================
-    const int q = warp;
+  } else if (warp < W_E2) {
+    // ============================ E1: Z^T_h -> dZ^T_h (+ db, dWf per-thread sums) ============================
+    // thread = output feature n = 128 h + row; warp (q, hh) covers the 64 points [64 hh, 64 hh + 64) of the tile
+    const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;
-    float db_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float dwf_acc[O][4];
+    const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
+    float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]
 #pragma unroll
-    for (int oo = 0; oo < O; ++oo)
+    for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row];
+    float db_acc = 0.f;
+    float dwf_acc[O];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) dwf_acc[oo][b] = 0.f;
+    for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tt = t_begin + t;
       const int64_t jb = tt / n_o;
       const int64_t o_local = tt - jb * n_o;
-      const int64_t j = jb * TILE_M + row;
-      float d[O];
-#pragma unroll
-      for (int oo = 0; oo < O; ++oo) d[oo] = 0.f;
-      if (j < p.n_inner) {
-        const float* src = p.dout + (o_local * p.stride_o + j * p.stride_j) * O;
-#pragma unroll
-        for (int oo = 0; oo < O; ++oo) d[oo] = src[oo];
-      }
+      const float* ds = reinterpret_cast<const float*>(smem_gen + SM_DOUT) + 64 * hh * O;   // this warp's 64 points
       ptx::mbar_wait(bar_zfull, t & 1);
       ptx::tc_fence_after();
+      ptx::mbar_wait(bar_dsfull, t & 1);
       ptx::mbar_wait(bar_dzempty, (t & 1) ^ 1);
+      uint8_t* dzrow = smem_gen + SM_DZ + hh * CH;                // 64 points = one 128-byte row of this chunk
 #pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < 2; ++b) {
+        // d0[i] = dout[p_i, 0]  (O == 1)   |   g[i] = sum_o dout[p_i, o] * wfs[o][n]  (O > 1)
+        // (loads in flight while the TMEM load completes)
+        float g[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float* dp = ds + (b * 32 + i) * O;                  // warp-uniform shared-memory address: broadcast
+          if (O == 1) {
+            g[i] = dp[0];
+          } else {
+            float acc = 0.f;
+#pragma unroll
+            for (int oo = 0; oo < O; ++oo) acc = fmaf(dp[oo], wfs_n[oo], acc);
+            g[i] = acc;
+          }
+        }
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tZ + ((uint32_t)(q * 32) << 16) + b * 32, r);
+        ptx::tmem_ld_32x32b_x32(tZ + ((uint32_t)(q * 32) << 16) + hh * 64 + b * 32, r);
         ptx::tmem_ld_wait();
-        if (b == 3) {                              // every Z column of this tile is in registers
+        if (b == 1) {                              // every Z^T column of this warp is in registers
           ptx::tc_fence_before();
           ptx::mbar_arrive(bar_zempty);
         }
-        float dzv[32], av[32];
+        float dzv[32];
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + b * 32 + i4 * 4);
-          float4 ww[O];
-#pragma unroll
-          for (int oo = 0; oo < O; ++oo) ww[oo] = *reinterpret_cast<const float4*>(s_wfs + oo * 128 + b * 32 + i4 * 4);
-          const float bs[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = i4 * 4 + e;
-            const float z = __uint_as_float(r[i]);
-            float g = 0.f;
-#pragma unroll
-            for (int oo = 0; oo < O; ++oo) {
-              const float wv = e == 0 ? ww[oo].x : (e == 1 ? ww[oo].y : (e == 2 ? ww[oo].z : ww[oo].w));
-              g = fmaf(d[oo], wv, g);
-            }
-            if (ACT == COORDX_ACT_SINE) {
-              const float th = fmaf(z, p.S, bs[e]);
-              dzv[i] = g * __cosf(th);
-              if (DO_DW) av[i] = __sinf(th);
+        for (int i = 0; i < 32; ++i) {
+          const float z = __uint_as_float(r[i]);
+          const float gw = O == 1 ? g[i] * wfs_n[0] : g[i];
+          float av;                                // activation value (for dWf), derivative folded into dzv
+          if (ACT == COORDX_ACT_SINE) {
+            const float th = fmaf(z, p.S, bias_n);
+            dzv[i] = gw * __cosf(th);
+            av = DO_DW ? __sinf(th) : 0.f;
+          } else {
+            const float pre = z + bias_n;
+            dzv[i] = pre > 0.f ? gw : 0.f;
+            av = fmaxf(pre, 0.f);
+          }
+          if (DO_DW) {
+            db_acc += dzv[i];
+            if (O == 1) {
+              dwf_acc[0] = fmaf(g[i], av, dwf_acc[0]);
             } else {
-              const float pre = z + bs[e];
-              dzv[i] = pre > 0.f ? g : 0.f;
-              if (DO_DW) av[i] = fmaxf(pre, 0.f);
+              const float* dp = ds + (b * 32 + i) * O;
+#pragma unroll
+              for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
             }
           }
         }
-        // dZ_h columns 32b..32b+31 of this row -> 4 swizzled 16-byte pieces
-        uint8_t* dzrow = smem_gen + SM_DZ + (b >> 1) * CH;
+        // points 32b .. 32b+31 of row n -> 4 swizzled 16-byte pieces
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
           uint4 w;
@@ -424,29 +462,16 @@ trunk_bwd_tc_kernel(const BwdParams p) {
           w.y = Pack<T>::pack(dzv[pc * 8 + 2], dzv[pc * 8 + 3]);
           w.z = Pack<T>::pack(dzv[pc * 8 + 4], dzv[pc * 8 + 5]);
           w.w = Pack<T>::pack(dzv[pc * 8 + 6], dzv[pc * 8 + 7]);
-          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, (b & 1) * 32 + pc * 8)) = w;
-        }
-        if (DO_DW) {
-#pragma unroll
-          for (int oo = 0; oo < O; ++oo) {
-            float tmp[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) tmp[i] = d[oo] * av[i];
-            dwf_acc[oo][b] += warp_transpose_reduce(tmp, lane);
-          }
-          db_acc[b] += warp_transpose_reduce(dzv, lane);
+          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, b * 32 + pc * 8)) = w;
         }
       }
       ptx::fence_proxy_async();
-      ptx::mbar_arrive(bar_dzfull);
+      ptx::mbar_arrive(bar_dzfull + 8 * hh);
     }
     if (DO_DW && my_tiles > 0) {
+      atomicAdd(p.db + h * 128 + row, db_acc);
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        atomicAdd(p.db + h * 128 + b * 32 + lane, db_acc[b]);
-#pragma unroll
-        for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + b * 32 + lane, dwf_acc[oo][b]);
-      }
+      for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
     }
   } else {
     // ============================ E2: dH pieces -> d rowvec ============================
@@ -516,7 +541,7 @@ trunk_bwd_tc_kernel(const BwdParams p) {
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == W_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
