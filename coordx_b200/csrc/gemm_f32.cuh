@@ -262,10 +262,36 @@ colsum_kernel(const float* __restrict__ dZ, int64_t ld, int M, int N, float scal
   }
 }
 
+// narrow matrices (N <= 8, contiguous rows): every thread walks the flat array with a stride that is a
+// multiple of N, so its column is fixed; one shared-memory atomic per thread, one global atomic per column per CTA
+__global__ void __launch_bounds__(256)
+colsum_narrow_kernel(const float* __restrict__ dZ, int64_t total, int N, float scale, float* __restrict__ db) {
+  __shared__ float red[8];
+  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t stride = (nthreads + N - 1) / N * N;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float s = 0.f;
+  for (int64_t i = i0; i < total; i += stride) s += dZ[i];
+  atomicAdd(&red[i0 % N], s);
+  __syncthreads();
+  if (threadIdx.x < N) atomicAdd(&db[threadIdx.x], red[threadIdx.x] * scale);
+}
+
 static int bias_backward(const float* dZ, int64_t ld, int M, int N, float scale, float* db, cudaStream_t st) {
   if (M <= 0) return 0;
-  int rpb = 2048;
-  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, rpb));
+  if (N <= 8 && ld == N) {
+    const int64_t total = (int64_t)M * N;
+    const int blocks = (int)min((int64_t)148 * 8, cdiv(total, 256 * 4));
+    colsum_narrow_kernel<<<max(blocks, 1), 256, 0, st>>>(dZ, total, N, scale, db);
+    CX_LAUNCH_CHECK();
+    return 0;
+  }
+  // ~4 CTAs per SM: rows per block from the number of 32-column strips
+  const int64_t strips = cdiv(N, 32);
+  int rpb = (int)max((int64_t)32, cdiv((int64_t)M * strips, (int64_t)148 * 4));
+  dim3 grid((unsigned)strips, (unsigned)cdiv(M, rpb));
   colsum_kernel<<<grid, 256, 0, st>>>(dZ, ld, M, N, scale, db, rpb);
   CX_LAUNCH_CHECK();
   return 0;

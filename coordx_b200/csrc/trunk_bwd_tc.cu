@@ -27,7 +27,8 @@
 //   H     [128 pts   x 256 k_in] : B of G1 (K-major, N = pts)      and B of G3 (MN-major, N = k_in)
 //   dZ^T_h[128 n_out x 128 pts ] : A of G3 (K-major, M = n_out)    and A of G2 (MN-major, M = pts)
 //
-// CTA = 17 warps: 0-7 E1 (quadrant = warp % 4, point half = warp / 4) | 8-11 E2 | 12-15 producers | 16 MMA issuer.
+// CTA = 21 warps: 0-7 E1 (quadrant = warp % 4, point half = warp / 4) | 8-15 E2 (quadrant, column half) |
+// 16-19 producers | 20 MMA issuer.
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -80,8 +81,8 @@ constexpr uint32_t SM_INNER = 10 * CH;            // 4 chunks (64 KB)
 constexpr uint32_t SM_BAR = 14 * CH;
 constexpr uint32_t SM_DOUT = SM_BAR + 256;        // float dout[128 points][MAX_O] of the current tile (staged by the producers)
 constexpr uint32_t SM_TOTAL_B = SM_DOUT + TILE_M * MAX_O * 4;     // 231680 bytes <= 227 KB
-constexpr int BWD_THREADS = 17 * 32;
-constexpr int W_E2 = 8, W_PROD = 12, W_MMA = 16;  // first warp of each role
+constexpr int BWD_THREADS = 21 * 32;
+constexpr int W_E2 = 8, W_PROD = 16, W_MMA = 20;  // first warp of each role
 
 struct BwdParams {
   const uint8_t* w_img;      // full W image of the forward prep: 4 K-chunks of [256 rows x 128 B]
@@ -166,13 +167,13 @@ trunk_bwd_tc_kernel(const BwdParams p) {
   const uint32_t bar_dsfull = bar0 + 168;          // producers have staged dout of the tile (128)
   const uint32_t bar_dzempty = bar0 + 88;          // G2/G3 have read dZ         (commit)
   const uint32_t bar_dhfull = bar0 + 96;
-  const uint32_t bar_dhempty = bar0 + 104;         // E2 has read the dH piece   (128)
+  const uint32_t bar_dhempty = bar0 + 104;         // E2 has read the dH piece   (256)
   const uint32_t bar_w = bar0 + 112;
   const uint32_t bar_inner = bar0 + 120;
   const uint32_t bar_dwfull = bar0 + 128;
   const uint32_t tmem_slot = bar0 + 136;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SM_BAR + 136);
-  volatile int* e2_done = reinterpret_cast<volatile int*>(smem_gen + SM_BAR + 144);   // tiles fully reduced by E2 (x4 warps)
+  volatile int* e2_done = reinterpret_cast<volatile int*>(smem_gen + SM_BAR + 144);   // tiles fully reduced by E2 (x8 warps)
 
   const int h = blockIdx.x & 1;                    // half of the trunk's output features
   const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
@@ -195,7 +196,7 @@ trunk_bwd_tc_kernel(const BwdParams p) {
       ptx::mbar_init(bar_dsfull, 128);
       ptx::mbar_init(bar_dzempty, 1);
       ptx::mbar_init(bar_dhfull, 1);
-      ptx::mbar_init(bar_dhempty, 128);
+      ptx::mbar_init(bar_dhempty, 256);
       ptx::mbar_init(bar_w, 1);
       ptx::mbar_init(bar_inner, 1);
       ptx::mbar_init(bar_dwfull, 1);
@@ -340,7 +341,7 @@ trunk_bwd_tc_kernel(const BwdParams p) {
         ptx::named_bar_sync(1, 128);
         if (ptid == 0) {
           if (OP == COORDX_FUSE_PROD) {            // E2 multiplies dH by the inner block: wait until it is done with it
-            while (*e2_done < 4 * t) {
+            while (*e2_done < 8 * t) {
             }
           }
           ptx::fence_proxy_async();
@@ -402,7 +403,6 @@ trunk_bwd_tc_kernel(const BwdParams p) {
       ptx::mbar_wait(bar_zfull, t & 1);
       ptx::tc_fence_after();
       ptx::mbar_wait(bar_dsfull, t & 1);
-      ptx::mbar_wait(bar_dzempty, (t & 1) ^ 1);
       uint8_t* dzrow = smem_gen + SM_DZ + hh * CH;                // 64 points = one 128-byte row of this chunk
 #pragma unroll 1
       for (int b = 0; b < 2; ++b) {
@@ -454,7 +454,8 @@ trunk_bwd_tc_kernel(const BwdParams p) {
             }
           }
         }
-        // points 32b .. 32b+31 of row n -> 4 swizzled 16-byte pieces
+        // points 32b .. 32b+31 of row n -> 4 swizzled 16-byte pieces (the tensor core must be done with dZ(t-1))
+        if (b == 0) ptx::mbar_wait(bar_dzempty, (t & 1) ^ 1);
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
           uint4 w;
@@ -475,7 +476,8 @@ trunk_bwd_tc_kernel(const BwdParams p) {
     }
   } else {
     // ============================ E2: dH pieces -> d rowvec ============================
-    const int q = warp & 3;
+    // warp (q, eh): lane quadrant q (32 points), columns [64 eh, 64 eh + 64) of every 128-column dH piece
+    const int q = warp & 3, eh = (warp - W_E2) >> 2;
     const int row = q * 32 + lane;
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tt = t_begin + t;
@@ -488,11 +490,11 @@ trunk_bwd_tc_kernel(const BwdParams p) {
         ptx::mbar_wait(bar_dhfull, u & 1);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 2 * eh; b < 2 * eh + 2; ++b) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(tDH + ((uint32_t)(q * 32) << 16) + b * 32, r);
           ptx::tmem_ld_wait();
-          if (b == 3) {
+          if (b == 2 * eh + 1) {
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_dhempty);
           }
