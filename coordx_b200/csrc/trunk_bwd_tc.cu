@@ -74,19 +74,21 @@ prep_inner_kernel(const float* __restrict__ feat, int64_t n, uint8_t* __restrict
 
 
 constexpr uint32_t CH = 16384;                    // one [128 rows x 128 B] SWIZZLE_128B chunk
-constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB)
-constexpr uint32_t SM_H = 4 * CH;                 // 4 chunks (64 KB)
-constexpr uint32_t SM_DZ = 8 * CH;                // 2 chunks (32 KB)
-constexpr uint32_t SM_INNER = 10 * CH;            // 4 chunks (64 KB)
+constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB): this CTA's 128 output features of W
+// dH pass:  H 4 chunks | dZ^T 2 chunks | inner block 4 chunks          dW pass:  H stage 0 | H stage 1 | dZ^T 2 chunks
+constexpr uint32_t SM_H = 4 * CH;
+constexpr uint32_t SM_DZ_DH = 8 * CH, SM_INNER = 10 * CH;
+constexpr uint32_t SM_H1 = 8 * CH, SM_DZ_DW = 12 * CH;
 constexpr uint32_t SM_BAR = 14 * CH;
 constexpr uint32_t SM_DOUT = SM_BAR + 256;        // float dout[128 points][MAX_O] of the current tile (staged by the producers)
 constexpr uint32_t SM_TOTAL_B = SM_DOUT + TILE_M * MAX_O * 4;     // 231680 bytes <= 227 KB
-constexpr int BWD_THREADS = 21 * 32;
-constexpr int W_E2 = 8, W_PROD = 16, W_MMA = 20;  // first warp of each role
+// dH pass: 0-7 E1 | 8-15 E2 | 16-19 producers | 20 MMA.   dW pass: 0-7 E1 | 8-15 producers | 16 MMA.
+constexpr int DH_THREADS = 21 * 32, DW_THREADS = 17 * 32;
 
 struct BwdParams {
   const uint8_t* w_img;      // full W image of the forward prep: 4 K-chunks of [256 rows x 128 B]
-  const uint8_t* inner_img;  // inner axis table, per 128-row block 4 K-chunks [128 x 128 B]
+  const uint8_t* inner_img;  // inner axis table, per 128-row block 4 K-chunks [128 x 128 B]   (dH pass)
+  const float* inner_f32;    // the same table as fp32 [n_inner, 256]                           (dW pass)
   const float* consts;       // [256] bias' then [MAX_O][256] wfs (see prep_bwd_consts_kernel)
   const float* outer0;
   const float* outer1;
@@ -149,31 +151,171 @@ __device__ __forceinline__ void unpack8<__half>(const uint4& q, float (&f)[8]) {
   }
 }
 
-template <typename T, int OP, int ACT, int O, bool DO_DW>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
-trunk_bwd_tc_kernel(const BwdParams p) {
+
+// barrier block (byte offsets from SM_BAR), shared by the two kernels
+struct Bars {
+  uint32_t full, empty;      // [4] H chunk (dH pass) / [2] H stage (dW pass)
+  uint32_t zfull, zempty;    // [2] Z^T accumulators
+  uint32_t dzfull;           // [2] 64-point chunks of dZ^T written by E1 (128 each)
+  uint32_t dzempty;          // tensor core done with dZ^T (commit)
+  uint32_t dhfull, dhempty;  // dH accumulator (dH pass)
+  uint32_t dsfull, dsempty;  // dout staging
+  uint32_t w, inner, dwfull, tmem_slot, e2_done;
+  __device__ explicit Bars(uint32_t b0)
+      : full(b0), empty(b0 + 32), zfull(b0 + 64), zempty(b0 + 80), dzfull(b0 + 96), dzempty(b0 + 112), dhfull(b0 + 120),
+        dhempty(b0 + 128), dsfull(b0 + 136), dsempty(b0 + 144), w(b0 + 152), inner(b0 + 160), dwfull(b0 + 168),
+        tmem_slot(b0 + 176), e2_done(b0 + 184) {}
+};
+
+// ---------------------------------------------------------------------------------
+// E1 (8 warps, both passes): Z^T_h (TMEM, lanes = output feature n) -> dZ^T_h (16-bit tile in shared memory).
+// thread = output feature n = 128 h + row; warp (q, hh) covers the 64 points [64 hh, 64 hh + 64) of the tile.
+// bias'[n], wfs[o][n] are registers; db[n] and dWf[o][n] are per-thread running sums (no cross-lane reduction).
+// Only the dW pass needs sin (for dWf); the dH passes evaluate cos alone: half the MUFU work.
+// ---------------------------------------------------------------------------------
+template <typename T, int ACT, int O, bool DO_DW>
+__device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint8_t* smem_gen, uint32_t tmem_z0, uint32_t sm_dz,
+                                         int h, int warp, int lane, int my_tiles) {
+  const int q = warp & 3, hh = warp >> 2;
+  const int row = q * 32 + lane;
+  const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
+  float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]
+#pragma unroll
+  for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row];
+  float db_acc = 0.f;
+  float dwf_acc[O];
+#pragma unroll
+  for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = 0.f;
+  const float* ds = reinterpret_cast<const float*>(smem_gen + SM_DOUT) + 64 * hh * O;   // this warp's 64 points
+  uint8_t* dzrow = smem_gen + sm_dz + hh * CH;                  // 64 points = one 128-byte row of this chunk
+  for (int t = 0; t < my_tiles; ++t) {
+    const uint32_t zb = t & 1, zuse = t >> 1;
+    ptx::mbar_wait(B.dsfull, t & 1);
+    ptx::mbar_wait(B.zfull + 8 * zb, zuse & 1);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int b = 0; b < 2; ++b) {
+      // d0[i] = dout[p_i, 0]  (O == 1)   |   g[i] = sum_o dout[p_i, o] * wfs[o][n]  (O > 1)
+      float g[32];
+      if (O == 1) {
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {                        // warp-uniform shared-memory addresses: broadcast LDS.128
+          const float4 d4 = *reinterpret_cast<const float4*>(ds + b * 32 + i4 * 4);
+          g[i4 * 4 + 0] = d4.x; g[i4 * 4 + 1] = d4.y; g[i4 * 4 + 2] = d4.z; g[i4 * 4 + 3] = d4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float* dp = ds + (b * 32 + i) * O;
+          float acc = 0.f;
+#pragma unroll
+          for (int oo = 0; oo < O; ++oo) acc = fmaf(dp[oo], wfs_n[oo], acc);
+          g[i] = acc;
+        }
+      }
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_z0 + zb * 128 + ((uint32_t)(q * 32) << 16) + hh * 64 + b * 32, r);
+      ptx::tmem_ld_wait();
+      if (b == 1) {                                // every Z^T column of this warp is in registers
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(B.zempty + 8 * zb);
+      }
+      float dzv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float z = __uint_as_float(r[i]);
+        const float gw = O == 1 ? g[i] * wfs_n[0] : g[i];
+        float av;                                  // activation value (for dWf); the derivative is folded into dzv
+        if (ACT == COORDX_ACT_SINE) {
+          const float th = fmaf(z, p.S, bias_n);
+          dzv[i] = gw * __cosf(th);
+          av = DO_DW ? __sinf(th) : 0.f;
+        } else {
+          const float pre = z + bias_n;
+          dzv[i] = pre > 0.f ? gw : 0.f;
+          av = fmaxf(pre, 0.f);
+        }
+        if (DO_DW) {
+          db_acc += dzv[i];
+          if (O == 1) {
+            dwf_acc[0] = fmaf(g[i], av, dwf_acc[0]);
+          } else {
+            const float* dp = ds + (b * 32 + i) * O;
+#pragma unroll
+            for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
+          }
+        }
+      }
+      if (b == 1 && (DO_DW && O > 1 ? false : true)) ptx::mbar_arrive(B.dsempty);   // last read of the staged dout
+      // points 32b .. 32b+31 of row n -> 4 swizzled 16-byte pieces (the tensor core must be done with dZ(t-1))
+      if (b == 0) ptx::mbar_wait(B.dzempty, (t & 1) ^ 1);
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        uint4 w;
+        w.x = Pack<T>::pack(dzv[pc * 8 + 0], dzv[pc * 8 + 1]);
+        w.y = Pack<T>::pack(dzv[pc * 8 + 2], dzv[pc * 8 + 3]);
+        w.z = Pack<T>::pack(dzv[pc * 8 + 4], dzv[pc * 8 + 5]);
+        w.w = Pack<T>::pack(dzv[pc * 8 + 6], dzv[pc * 8 + 7]);
+        *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, b * 32 + pc * 8)) = w;
+      }
+    }
+    if (DO_DW && O > 1) ptx::mbar_arrive(B.dsempty);
+    ptx::fence_proxy_async();
+    ptx::mbar_arrive(B.dzfull + 8 * hh);
+  }
+  if (DO_DW && my_tiles > 0) {
+    atomicAdd(p.db + h * 128 + row, db_acc);
+#pragma unroll
+    for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
+  }
+}
+
+// one element of a 16-bit operand tile as fp32
+template <typename T>
+__device__ __forceinline__ float ld_el(const uint8_t* p);
+template <>
+__device__ __forceinline__ float ld_el<__nv_bfloat16>(const uint8_t* p) {
+  return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(p)) << 16);
+}
+template <>
+__device__ __forceinline__ float ld_el<__half>(const uint8_t* p) { return __half2float(*reinterpret_cast<const __half*>(p)); }
+
+// rowvec(o) piece: 8 fp32 values of outer0[i0] (+|*) outer1[i1] starting at column k0
+template <int OP>
+__device__ __forceinline__ void load_rowvec8(const BwdParams& p, int64_t o, int k0, float4& x0, float4& x1) {
+  int64_t i0 = o, i1 = 0;
+  if (p.outer1) { i0 = o / p.n_outer1; i1 = o - i0 * p.n_outer1; }
+  x0 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + k0);
+  x1 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + k0 + 4);
+  if (p.outer1) {
+    const float4 y0 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + k0);
+    const float4 y1 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + k0 + 4);
+    if (OP == COORDX_FUSE_PROD) {
+      x0.x *= y0.x; x0.y *= y0.y; x0.z *= y0.z; x0.w *= y0.w;
+      x1.x *= y1.x; x1.y *= y1.y; x1.z *= y1.z; x1.w *= y1.w;
+    } else {
+      x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
+      x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
+    }
+  }
+}
+
+// =================================================================================
+// dW pass:  G1 Z^T = W_h H^T  ->  E1 (sin + cos; db, dWf)  ->  G3 dW_h += dZ^T H     (dW, db, dWf)
+// TMEM: Z^T x2 (cols 0, 128) | dW_h (cols 256..511).  H double-buffered in shared memory, the inner block lives in
+// the producers' registers (as in the forward kernel), so G1(t+1) overlaps E1(t) and G3(t-1).
+// =================================================================================
+template <typename T, int OP, int ACT, int O>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+trunk_bwd_dw_kernel(const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem_gen = smem_raw;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar0 = smem_base + SM_BAR;
-  const uint32_t bar_full = bar0;                  // [4] H chunk written        (128 producers)
-  const uint32_t bar_empty = bar0 + 32;            // [4] H chunk no longer read (tcgen05.commit)
-  const uint32_t bar_zfull = bar0 + 64;
-  const uint32_t bar_zempty = bar0 + 72;           // E1 has read Z^T            (256)
-  const uint32_t bar_dzfull = bar0 + 152;          // [2] E1 has written the 64-point chunk of dZ^T (128 each)
-  const uint32_t bar_dsfull = bar0 + 168;          // producers have staged dout of the tile (128)
-  const uint32_t bar_dzempty = bar0 + 88;          // G2/G3 have read dZ         (commit)
-  const uint32_t bar_dhfull = bar0 + 96;
-  const uint32_t bar_dhempty = bar0 + 104;         // E2 has read the dH piece   (256)
-  const uint32_t bar_w = bar0 + 112;
-  const uint32_t bar_inner = bar0 + 120;
-  const uint32_t bar_dwfull = bar0 + 128;
-  const uint32_t tmem_slot = bar0 + 136;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SM_BAR + 136);
-  volatile int* e2_done = reinterpret_cast<volatile int*>(smem_gen + SM_BAR + 144);   // tiles fully reduced by E2 (x8 warps)
+  const Bars B(smem_base + SM_BAR);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SM_BAR + 176);
+  constexpr int W_PROD = 8, W_MMA = 16;
 
   const int h = blockIdx.x & 1;                    // half of the trunk's output features
   const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
@@ -185,115 +327,305 @@ trunk_bwd_tc_kernel(const BwdParams p) {
 
   if (warp == W_MMA) {
     if (lane == 0) {
-      for (int c = 0; c < 4; ++c) {
-        ptx::mbar_init(bar_full + 8 * c, 128);
-        ptx::mbar_init(bar_empty + 8 * c, 1);
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(B.full + 8 * c, 8);         // 8 producer warps
+        ptx::mbar_init(B.empty + 8 * c, 1);
+        ptx::mbar_init(B.zfull + 8 * c, 1);
+        ptx::mbar_init(B.zempty + 8 * c, 256);
+        ptx::mbar_init(B.dzfull + 8 * c, 128);
       }
-      ptx::mbar_init(bar_zfull, 1);
-      ptx::mbar_init(bar_zempty, 256);
-      ptx::mbar_init(bar_dzfull, 128);
-      ptx::mbar_init(bar_dzfull + 8, 128);
-      ptx::mbar_init(bar_dsfull, 128);
-      ptx::mbar_init(bar_dzempty, 1);
-      ptx::mbar_init(bar_dhfull, 1);
-      ptx::mbar_init(bar_dhempty, 256);
-      ptx::mbar_init(bar_w, 1);
-      ptx::mbar_init(bar_inner, 1);
-      ptx::mbar_init(bar_dwfull, 1);
-      *e2_done = 0;
+      ptx::mbar_init(B.dzempty, 1);
+      ptx::mbar_init(B.dsfull, 128);
+      ptx::mbar_init(B.dsempty, 256);
+      ptx::mbar_init(B.w, 1);
+      ptx::mbar_init(B.dwfull, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_alloc(B.tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
-  const uint32_t tZ = tmem_base, tDH = tmem_base + 128, tDW = tmem_base + 256;
+  const uint32_t tZ = tmem_base, tDW = tmem_base + 256;
 
   if (warp == W_MMA) {
     // ============================ MMA issuer ============================
     if (lane == 0 && my_tiles > 0) {
-      ptx::mbar_arrive_expect_tx(bar_w, 4 * CH);
+      ptx::mbar_arrive_expect_tx(B.w, 4 * CH);
       for (int kc = 0; kc < 4; ++kc)
-        ptx::bulk_g2s(smem_base + SM_W + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, bar_w);
-      ptx::mbar_wait(bar_w, 0);
-      constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 0);
-      constexpr uint32_t id_g2 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 1);   // A = dZ (M = pts) MN-major, B = W_h (N = k_in) MN-major
+        ptx::bulk_g2s(smem_base + SM_W + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, B.w);
+      ptx::mbar_wait(B.w, 0);
+      constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 0);   // A = W_h (M = n_out), B = H (N = points), both K-major
       constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (M = n_out) K-major, B = H (N = k_in) MN-major
-      uint32_t dh_uses = 0;
-      auto issue_g2 = [&](int piece) {
-        ptx::mbar_wait(bar_dhempty, (dh_uses & 1) ^ 1);
+      auto issue_g1 = [&](int t) {
+        const uint32_t zb = t & 1, use = t >> 1;
+        ptx::mbar_wait(B.zempty + 8 * zb, (use & 1) ^ 1);
+        ptx::mbar_wait(B.full + 8 * zb, use & 1);
         ptx::tc_fence_after();
+        const uint32_t hs = smem_base + (zb ? SM_H1 : SM_H);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {           // K = 128 n_out of this half = 16 rows of the dZ^T tile per step
-          const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_DZ + ks * 2048, CH);
-          const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_W + piece * 2 * CH + ks * 2048, CH);
-          ptx::mma_f16_ss(tDH, a, b, id_g2, ks != 0);
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t off = (k >> 2) * CH + (k & 3) * 32;
+          ptx::mma_f16_ss(tZ + zb * 128, ptx::umma_desc_k_sw128(smem_base + SM_W + off), ptx::umma_desc_k_sw128(hs + off), id_g1, k != 0);
         }
-        ptx::mma_commit(bar_dhfull);
-        ++dh_uses;
+        ptx::mma_commit(B.zfull + 8 * zb);
       };
-      for (int t = 0; t < my_tiles; ++t) {
-        // G2b(t-1), the second dH piece of the previous tile, is software-pipelined behind G1(t) -
-        // except across a change of inner block: there the producers wait for E2(t-1) before they
-        // overwrite the inner block, so G2b(t-1) must not wait for their H(t)
-        const bool defer = t > 0 && (t_begin + t) / n_o == (t_begin + t - 1) / n_o;
-        if (t > 0 && !defer) {
-          issue_g2(1);
-          ptx::mma_commit(bar_dzempty);
-        }
-        // ---- G1(t): Z^T_h = W_h H^T   (A = W_h, M = n_out; B = H, N = points)
-        ptx::mbar_wait(bar_zempty, (t & 1) ^ 1);
-        ptx::tc_fence_after();
+      auto issue_g3 = [&](int t) {
+        const uint32_t hs = smem_base + ((t & 1) ? SM_H1 : SM_H);
 #pragma unroll 1
-        for (int kc = 0; kc < 4; ++kc) {
-          ptx::mbar_wait(bar_full + 8 * kc, t & 1);
+        for (int c = 0; c < 2; ++c) {              // K = 128 points, 16 per step; starts on the first 64-point chunk of dZ^T
+          ptx::mbar_wait(B.dzfull + 8 * c, t & 1);
           ptx::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(tZ, ptx::umma_desc_k_sw128(smem_base + SM_W + kc * CH + k * 32),
-                            ptx::umma_desc_k_sw128(smem_base + SM_H + kc * CH + k * 32), id_g1, (kc | k) != 0);
-          if (!DO_DW) ptx::mma_commit(bar_empty + 8 * kc);
-        }
-        ptx::mma_commit(bar_zfull);
-        if (defer) {
-          issue_g2(1);
-          ptx::mma_commit(bar_dzempty);
-        }
-        // ---- G3(t): dW_h += dZ^T_h H   (K = 128 points, 16 per step; starts on the first 64-point chunk of dZ^T)
-        if (DO_DW) {
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            ptx::mbar_wait(bar_dzfull + 8 * c, t & 1);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int ks = c * 4 + k;
-              const uint64_t a = ptx::umma_desc_k_sw128(smem_base + SM_DZ + c * CH + k * 32);
-              const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_H + ks * 2048, CH);
-              ptx::mma_f16_ss(tDW, a, b, id_g3, (t | ks) != 0);
-            }
+          for (int k = 0; k < 4; ++k) {
+            const int ks = c * 4 + k;
+            ptx::mma_f16_ss(tDW, ptx::umma_desc_k_sw128(smem_base + SM_DZ_DW + c * CH + k * 32),
+                            ptx::umma_desc_mn_sw128(hs + ks * 2048, CH), id_g3, (t | ks) != 0);
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) ptx::mma_commit(bar_empty + 8 * c);
-        } else {
-          ptx::mbar_wait(bar_dzfull, t & 1);
-          ptx::mbar_wait(bar_dzfull + 8, t & 1);
-          ptx::tc_fence_after();
         }
-        // ---- G2a(t)
-        issue_g2(0);
+        ptx::mma_commit(B.empty + 8 * (t & 1));    // H stage free for the producers
+        ptx::mma_commit(B.dzempty);                // dZ^T tile free for E1
+      };
+      // G1(t+1) is issued AHEAD of G3(t): E1 is the longest stage, so its input must never queue behind G3 in the
+      // in-order tensor pipe (polling "whichever is ready first" was measured 18 % slower for exactly that reason)
+      issue_g1(0);
+      for (int t = 0; t < my_tiles; ++t) {
+        if (t + 1 < my_tiles) issue_g1(t + 1);
+        issue_g3(t);
       }
-      issue_g2(1);
-      ptx::mma_commit(bar_dzempty);
-      ptx::mma_commit(bar_dwfull);
+      ptx::mma_commit(B.dwfull);
     }
     __syncwarp();
   } else if (warp >= W_PROD) {
-    // ============================ producers: H tile ============================
+    // ============================ producers: H tile (inner block piece in registers) ============================
+    // thread (g = lane, rg = warp - 8) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows 16 rg .. 16 rg + 15
+    const int g = lane, rg = warp - W_PROD;
+    const int ptid = threadIdx.x - W_PROD * 32;    // 0..255; the first 128 also stage dout
+    uint32_t in[16][4];
+    int64_t cur_jb = -1;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int64_t tt = t_begin + t;
+      const int64_t jb = tt / n_o;
+      const int64_t o_local = tt - jb * n_o;
+      uint32_t rv[4];
+      {
+        float4 x0, x1;
+        load_rowvec8<OP>(p, p.o_begin + o_local, 8 * g, x0, x1);      // L1 hit: prefetched during the previous tile
+        rv[0] = Pack<T>::pack(x0.x, x0.y);
+        rv[1] = Pack<T>::pack(x0.z, x0.w);
+        rv[2] = Pack<T>::pack(x1.x, x1.y);
+        rv[3] = Pack<T>::pack(x1.z, x1.w);
+      }
+      if (t + 1 < my_tiles) {                      // next tile's rowvec -> L1 while this tile is produced (no registers held)
+        const int64_t tn = tt + 1, jn = tn / n_o;
+        const int64_t on = p.o_begin + (tn - jn * n_o);
+        const int64_t i0 = p.outer1 ? on / p.n_outer1 : on;
+        ptx::prefetch_l1(p.outer0 + i0 * HD + 8 * g);
+        if (p.outer1) ptx::prefetch_l1(p.outer1 + (on - i0 * p.n_outer1) * HD + 8 * g);
+      }
+      float dreg[O];
+#pragma unroll
+      for (int oo = 0; oo < O; ++oo) dreg[oo] = 0.f;
+      if (ptid < TILE_M) {
+        const int64_t j = jb * TILE_M + ptid;
+        if (j < p.n_inner) {
+#pragma unroll
+          for (int oo = 0; oo < O; ++oo) dreg[oo] = __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo);
+        }
+      }
+      if (jb != cur_jb) {
+        uint32_t chain = 0;                        // batches of 4 rows chained through an opaque zero: bounds the loads in flight
+#pragma unroll
+        for (int r4 = 0; r4 < 16; r4 += 4) {
+          float4 v0[4], v1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t j = jb * TILE_M + rg * 16 + r4 + u;
+            v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v1[u] = v0[u];
+            if (j < p.n_inner) {
+              const float* src = p.inner_f32 + j * HD + 8 * g + chain;
+              v0[u] = *reinterpret_cast<const float4*>(src);
+              v1[u] = *reinterpret_cast<const float4*>(src + 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            in[r4 + u][0] = Pack<T>::pack(v0[u].x, v0[u].y);
+            in[r4 + u][1] = Pack<T>::pack(v0[u].z, v0[u].w);
+            in[r4 + u][2] = Pack<T>::pack(v1[u].x, v1[u].y);
+            in[r4 + u][3] = Pack<T>::pack(v1[u].z, v1[u].w);
+          }
+          asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(in[r4 + 3][3]));
+        }
+        cur_jb = jb;
+      }
+      const uint32_t st = t & 1, use = t >> 1;
+      ptx::mbar_wait(B.empty + 8 * st, (use & 1) ^ 1);
+      uint8_t* dst = smem_gen + (st ? SM_H1 : SM_H) + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        uint4 w;
+        w.x = fuse2<T, OP>(in[r][0], rv[0]);
+        w.y = fuse2<T, OP>(in[r][1], rv[1]);
+        w.z = fuse2<T, OP>(in[r][2], rv[2]);
+        w.w = fuse2<T, OP>(in[r][3], rv[3]);
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(B.full + 8 * st);
+      if (ptid < TILE_M) {
+        ptx::mbar_wait(B.dsempty, (t & 1) ^ 1);    // E1(t-1) has read its dout
+        float* ds = reinterpret_cast<float*>(smem_gen + SM_DOUT) + ptid * O;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo) ds[oo] = dreg[oo];
+        ptx::mbar_arrive(B.dsfull);
+      }
+    }
+  } else {
+    e1_stage<T, ACT, O, true>(p, B, smem_gen, tZ, SM_DZ_DW, h, warp, lane, my_tiles);
+    // ---- flush dW_h (accumulated over every tile of this CTA) with one atomic per element
+    if (my_tiles > 0) {
+      ptx::mbar_wait(B.dwfull, 0);
+      ptx::tc_fence_after();
+      const int q = warp & 3, ch = warp >> 2;
+      float* drow = p.dW + (size_t)(h * 128 + q * 32 + lane) * HD + ch * 128;
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tDW + ((uint32_t)(q * 32) << 16) + ch * 128 + b * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]));
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================
+// dH pass:  G1 Z^T = W_h H^T  ->  E1 (cos only)  ->  G2 dH = dZ W_h (256 columns)  ->  E2 d rowvec(o)
+// TMEM: Z^T x2 (cols 0, 128) | dH (cols 256..511).  Run twice: with the grid's own roles (gradient of the outer
+// axes' features) and with the roles swapped (gradient of the last axis' features).
+// =================================================================================
+template <typename T, int OP, int ACT, int O>
+__global__ void __launch_bounds__(DH_THREADS, 1)
+trunk_bwd_dh_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Bars B(smem_base + SM_BAR);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SM_BAR + 176);
+  volatile int* e2_done = reinterpret_cast<volatile int*>(smem_gen + SM_BAR + 184);   // tiles fully reduced by E2 (x8 warps)
+  constexpr int W_E2 = 8, W_PROD = 16, W_MMA = 20;
+
+  const int h = blockIdx.x & 1;
+  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int64_t t_begin = total * cta / n_cta;
+  const int64_t t_end = total * (cta + 1) / n_cta;
+  const int my_tiles = (int)(t_end - t_begin);
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int c = 0; c < 4; ++c) {
+        ptx::mbar_init(B.full + 8 * c, 128);
+        ptx::mbar_init(B.empty + 8 * c, 1);
+      }
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(B.zfull + 8 * c, 1);
+        ptx::mbar_init(B.zempty + 8 * c, 256);
+        ptx::mbar_init(B.dzfull + 8 * c, 128);
+      }
+      ptx::mbar_init(B.dzempty, 1);
+      ptx::mbar_init(B.dhfull, 1);
+      ptx::mbar_init(B.dhempty, 256);
+      ptx::mbar_init(B.dsfull, 128);
+      ptx::mbar_init(B.dsempty, 256);
+      ptx::mbar_init(B.w, 1);
+      ptx::mbar_init(B.inner, 1);
+      *e2_done = 0;
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(B.tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint32_t tZ = tmem_base, tDH = tmem_base + 256;
+
+  if (warp == W_MMA) {
+    // ============================ MMA issuer ============================
+    if (lane == 0 && my_tiles > 0) {
+      ptx::mbar_arrive_expect_tx(B.w, 4 * CH);
+      for (int kc = 0; kc < 4; ++kc)
+        ptx::bulk_g2s(smem_base + SM_W + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, B.w);
+      ptx::mbar_wait(B.w, 0);
+      constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 0);
+      constexpr uint32_t id_g2 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 1);   // A = W_h^T (M = k_in) MN-major, B = dZ^T (N = pts) MN-major
+      auto issue_g1 = [&](int t) {
+        const uint32_t zb = t & 1, use = t >> 1;
+        ptx::mbar_wait(B.zempty + 8 * zb, (use & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          ptx::mbar_wait(B.full + 8 * kc, t & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ss(tZ + zb * 128, ptx::umma_desc_k_sw128(smem_base + SM_W + kc * CH + k * 32),
+                            ptx::umma_desc_k_sw128(smem_base + SM_H + kc * CH + k * 32), id_g1, (kc | k) != 0);
+          ptx::mma_commit(B.empty + 8 * kc);
+        }
+        ptx::mma_commit(B.zfull + 8 * zb);
+      };
+      auto issue_g2 = [&](int t) {
+        ptx::mbar_wait(B.dzfull, t & 1);
+        ptx::mbar_wait(B.dzfull + 8, t & 1);
+        ptx::mbar_wait(B.dhempty, (t & 1) ^ 1);
+        ptx::tc_fence_after();
+        // dH^T[k_in, pts] = W_h^T dZ^T, two M-blocks of 128 input features; K = 128 n_out = 16 tile rows per step
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_W + blk * 2 * CH + ks * 2048, CH);
+            const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_DZ_DH + ks * 2048, CH);
+            ptx::mma_f16_ss(tDH + blk * 128, a, b, id_g2, ks != 0);
+          }
+        }
+        ptx::mma_commit(B.dhfull);
+        ptx::mma_commit(B.dzempty);
+      };
+      issue_g1(0);
+      for (int t = 0; t < my_tiles; ++t) {
+        // G1(t+1) is issued ahead of G2(t) - except across a change of inner block: there the producers wait for
+        // E2(t) before they overwrite the inner block, so H(t+1) cannot exist before G2(t) has been issued
+        const bool ahead = t + 1 < my_tiles && (t_begin + t + 1) / n_o == (t_begin + t) / n_o;
+        if (ahead) issue_g1(t + 1);
+        issue_g2(t);
+        if (!ahead && t + 1 < my_tiles) issue_g1(t + 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= W_PROD) {
+    // ============================ producers: H tile (inner block in shared memory, E2 needs it too) ============================
     const int ptid = threadIdx.x - W_PROD * 32;
     const int g8 = ptid & 7, r0 = ptid >> 3;
     const uint32_t piece_off = (uint32_t)(r0 >> 3) * 1024u + (uint32_t)(r0 & 7) * 128u + (uint32_t)((g8 ^ (r0 & 7)) << 4);
@@ -303,36 +635,19 @@ trunk_bwd_tc_kernel(const BwdParams p) {
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tt = t_begin + t;
       const int64_t jb = tt / n_o;
-      const int64_t o = p.o_begin + (tt - jb * n_o);
-      {
-        const int64_t i0 = o / p.n_outer1, i1 = o - i0 * p.n_outer1;
+      const int64_t o_local = tt - jb * n_o;
 #pragma unroll
-        for (int kc = 0; kc < NKC; ++kc) {
-          const int k0 = kc * KCHUNK + g8 * 8;
-          float4 x0 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + k0);
-          float4 x1 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + k0 + 4);
-          if (p.outer1) {
-            const float4 y0 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + k0);
-            const float4 y1 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + k0 + 4);
-            if (OP == COORDX_FUSE_PROD) {
-              x0.x *= y0.x; x0.y *= y0.y; x0.z *= y0.z; x0.w *= y0.w;
-              x1.x *= y1.x; x1.y *= y1.y; x1.z *= y1.z; x1.w *= y1.w;
-            } else {
-              x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
-              x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
-            }
-          }
-          rv[kc][0] = Pack<T>::pack(x0.x, x0.y);
-          rv[kc][1] = Pack<T>::pack(x0.z, x0.w);
-          rv[kc][2] = Pack<T>::pack(x1.x, x1.y);
-          rv[kc][3] = Pack<T>::pack(x1.z, x1.w);
-        }
+      for (int kc = 0; kc < NKC; ++kc) {
+        float4 x0, x1;
+        load_rowvec8<OP>(p, p.o_begin + o_local, kc * KCHUNK + g8 * 8, x0, x1);
+        rv[kc][0] = Pack<T>::pack(x0.x, x0.y);
+        rv[kc][1] = Pack<T>::pack(x0.z, x0.w);
+        rv[kc][2] = Pack<T>::pack(x1.x, x1.y);
+        rv[kc][3] = Pack<T>::pack(x1.z, x1.w);
       }
-      // dout of this thread's point (row ptid of the tile): loaded now, staged for E1 after the H chunks
       float dreg[O];
       {
         const int64_t j = jb * TILE_M + ptid;
-        const int64_t o_local = tt - jb * n_o;
 #pragma unroll
         for (int oo = 0; oo < O; ++oo)
           dreg[oo] = j < p.n_inner ? __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo) : 0.f;
@@ -345,17 +660,17 @@ trunk_bwd_tc_kernel(const BwdParams p) {
             }
           }
           ptx::fence_proxy_async();
-          ptx::mbar_arrive_expect_tx(bar_inner, INNER_BYTES);
+          ptx::mbar_arrive_expect_tx(B.inner, INNER_BYTES);
           for (uint32_t c = 0; c < INNER_BYTES; c += CH)
-            ptx::bulk_g2s(smem_base + SM_INNER + c, p.inner_img + (size_t)jb * INNER_BYTES + c, CH, bar_inner);
+            ptx::bulk_g2s(smem_base + SM_INNER + c, p.inner_img + (size_t)jb * INNER_BYTES + c, CH, B.inner);
         }
-        ptx::mbar_wait(bar_inner, inner_phase);
+        ptx::mbar_wait(B.inner, inner_phase);
         inner_phase ^= 1;
         cur_jb = jb;
       }
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
-        ptx::mbar_wait(bar_empty + 8 * kc, (t & 1) ^ 1);
+        ptx::mbar_wait(B.empty + 8 * kc, (t & 1) ^ 1);
         const uint8_t* src = smem_gen + SM_INNER + kc * CH + piece_off;
         uint8_t* dst = smem_gen + SM_H + kc * CH + piece_off;
         uint4 v[8];
@@ -371,173 +686,59 @@ trunk_bwd_tc_kernel(const BwdParams p) {
           *reinterpret_cast<uint4*>(dst + i * 2048) = w;
         }
         ptx::fence_proxy_async();
-        ptx::mbar_arrive(bar_full + 8 * kc);
+        ptx::mbar_arrive(B.full + 8 * kc);
       }
-      // E1(t-1) has read its dout (it arrives on zempty after its last read); G1(t) runs meanwhile
-      ptx::mbar_wait(bar_zempty, (t & 1) ^ 1);
+      ptx::mbar_wait(B.dsempty, (t & 1) ^ 1);      // E1(t-1) has read its dout
       {
         float* ds = reinterpret_cast<float*>(smem_gen + SM_DOUT) + ptid * O;
 #pragma unroll
         for (int oo = 0; oo < O; ++oo) ds[oo] = dreg[oo];
       }
-      ptx::mbar_arrive(bar_dsfull);
+      ptx::mbar_arrive(B.dsfull);
     }
   } else if (warp < W_E2) {
-    // ============================ E1: Z^T_h -> dZ^T_h (+ db, dWf per-thread sums) ============================
-    // thread = output feature n = 128 h + row; warp (q, hh) covers the 64 points [64 hh, 64 hh + 64) of the tile
-    const int q = warp & 3, hh = warp >> 2;
-    const int row = q * 32 + lane;
-    const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
-    float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]
-#pragma unroll
-    for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row];
-    float db_acc = 0.f;
-    float dwf_acc[O];
-#pragma unroll
-    for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = 0.f;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int64_t tt = t_begin + t;
-      const int64_t jb = tt / n_o;
-      const int64_t o_local = tt - jb * n_o;
-      const float* ds = reinterpret_cast<const float*>(smem_gen + SM_DOUT) + 64 * hh * O;   // this warp's 64 points
-      ptx::mbar_wait(bar_zfull, t & 1);
-      ptx::tc_fence_after();
-      ptx::mbar_wait(bar_dsfull, t & 1);
-      uint8_t* dzrow = smem_gen + SM_DZ + hh * CH;                // 64 points = one 128-byte row of this chunk
-#pragma unroll 1
-      for (int b = 0; b < 2; ++b) {
-        // d0[i] = dout[p_i, 0]  (O == 1)   |   g[i] = sum_o dout[p_i, o] * wfs[o][n]  (O > 1)
-        // (loads in flight while the TMEM load completes)
-        float g[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float* dp = ds + (b * 32 + i) * O;                  // warp-uniform shared-memory address: broadcast
-          if (O == 1) {
-            g[i] = dp[0];
-          } else {
-            float acc = 0.f;
-#pragma unroll
-            for (int oo = 0; oo < O; ++oo) acc = fmaf(dp[oo], wfs_n[oo], acc);
-            g[i] = acc;
-          }
-        }
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tZ + ((uint32_t)(q * 32) << 16) + hh * 64 + b * 32, r);
-        ptx::tmem_ld_wait();
-        if (b == 1) {                              // every Z^T column of this warp is in registers
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(bar_zempty);
-        }
-        float dzv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float z = __uint_as_float(r[i]);
-          const float gw = O == 1 ? g[i] * wfs_n[0] : g[i];
-          float av;                                // activation value (for dWf), derivative folded into dzv
-          if (ACT == COORDX_ACT_SINE) {
-            const float th = fmaf(z, p.S, bias_n);
-            dzv[i] = gw * __cosf(th);
-            av = DO_DW ? __sinf(th) : 0.f;
-          } else {
-            const float pre = z + bias_n;
-            dzv[i] = pre > 0.f ? gw : 0.f;
-            av = fmaxf(pre, 0.f);
-          }
-          if (DO_DW) {
-            db_acc += dzv[i];
-            if (O == 1) {
-              dwf_acc[0] = fmaf(g[i], av, dwf_acc[0]);
-            } else {
-              const float* dp = ds + (b * 32 + i) * O;
-#pragma unroll
-              for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
-            }
-          }
-        }
-        // points 32b .. 32b+31 of row n -> 4 swizzled 16-byte pieces (the tensor core must be done with dZ(t-1))
-        if (b == 0) ptx::mbar_wait(bar_dzempty, (t & 1) ^ 1);
-#pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          uint4 w;
-          w.x = Pack<T>::pack(dzv[pc * 8 + 0], dzv[pc * 8 + 1]);
-          w.y = Pack<T>::pack(dzv[pc * 8 + 2], dzv[pc * 8 + 3]);
-          w.z = Pack<T>::pack(dzv[pc * 8 + 4], dzv[pc * 8 + 5]);
-          w.w = Pack<T>::pack(dzv[pc * 8 + 6], dzv[pc * 8 + 7]);
-          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, b * 32 + pc * 8)) = w;
-        }
-      }
-      ptx::fence_proxy_async();
-      ptx::mbar_arrive(bar_dzfull + 8 * hh);
-    }
-    if (DO_DW && my_tiles > 0) {
-      atomicAdd(p.db + h * 128 + row, db_acc);
-#pragma unroll
-      for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
-    }
+    e1_stage<T, ACT, O, false>(p, B, smem_gen, tZ, SM_DZ_DH, h, warp, lane, my_tiles);
   } else {
-    // ============================ E2: dH pieces -> d rowvec ============================
-    // warp (q, eh): lane quadrant q (32 points), columns [64 eh, 64 eh + 64) of every 128-column dH piece
-    const int q = warp & 3, eh = (warp - W_E2) >> 2;
-    const int row = q * 32 + lane;
+    // ============================ E2: dH^T -> d rowvec ============================
+    // dH is produced transposed too (lanes = input feature k): d rowvec(o)[k] = sum_p dH^T[k,p] * inner[p,k] is a
+    // per-thread sum over the 128 point columns - one atomic per thread per tile, no shuffles.
+    // warp (q, blk): k = 128 blk + 32 q + lane
+    const int q = warp & 3, blk = (warp - W_E2) >> 2;
+    const int k = blk * 128 + q * 32 + lane;
+    // inner[p][k] inside the swizzled block: chunk k / 64, row p, piece ((k % 64) / 8) ^ (p % 8), element k % 8
+    const uint8_t* icol = smem_gen + SM_INNER + (k >> 6) * CH + (k & 7) * 2;
+    uint32_t xoff[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) xoff[r] = (uint32_t)(r * 128) + (uint32_t)(((((k & 63) >> 3) ^ r) & 7) << 4);
     for (int t = 0; t < my_tiles; ++t) {
       const int64_t tt = t_begin + t;
       const int64_t jb = tt / n_o;
       const int64_t o_local = tt - jb * n_o;
-      float* dst = p.d_rv + o_local * HD;
+      ptx::mbar_wait(B.dhfull, t & 1);
+      ptx::tc_fence_after();
+      float acc = 0.f;
 #pragma unroll 1
-      for (int piece = 0; piece < 2; ++piece) {
-        const uint32_t u = 2u * (uint32_t)t + (uint32_t)piece;
-        ptx::mbar_wait(bar_dhfull, u & 1);
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int b = 2 * eh; b < 2 * eh + 2; ++b) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tDH + ((uint32_t)(q * 32) << 16) + b * 32, r);
-          ptx::tmem_ld_wait();
-          if (b == 2 * eh + 1) {
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(bar_dhempty);
-          }
-          const int k0 = piece * 128 + b * 32;     // k_in of column 0 of this batch
-          float v[32];
-          if (OP == COORDX_FUSE_PROD) {
-            const uint8_t* irow = smem_gen + SM_INNER + (k0 >> 6) * CH;
+      for (int b = 0; b < 4; ++b) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tDH + blk * 128 + ((uint32_t)(q * 32) << 16) + b * 32, r);
+        ptx::tmem_ld_wait();
+        if (b == 3) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(B.dhempty);
+        }
 #pragma unroll
-            for (int pc = 0; pc < 4; ++pc) {
-              const uint4 qv = *reinterpret_cast<const uint4*>(irow + ptx::sw128_offset(row, (k0 & 63) + pc * 8));
-              float f[8];
-              unpack8<T>(qv, f);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[pc * 8 + e] = __uint_as_float(r[pc * 8 + e]) * f[e];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          }
-          const float s = warp_transpose_reduce(v, lane);
-          atomicAdd(dst + k0 + lane, s);
+        for (int i = 0; i < 32; ++i) {
+          if (OP == COORDX_FUSE_PROD)
+            acc = fmaf(__uint_as_float(r[i]), ld_el<T>(icol + (b * 4 + (i >> 3)) * 1024 + xoff[i & 7]), acc);
+          else
+            acc += __uint_as_float(r[i]);
         }
       }
+      atomicAdd(p.d_rv + o_local * HD + k, acc);
       if (OP == COORDX_FUSE_PROD) {
         __syncwarp();
         if (lane == 0) atomicAdd(const_cast<int*>(e2_done), 1);
       }
-    }
-  }
-
-  // ---- flush dW_h (accumulated over every tile of this CTA) with one atomic per element
-  if (DO_DW && warp < 8 && my_tiles > 0) {
-    ptx::mbar_wait(bar_dwfull, 0);
-    ptx::tc_fence_after();
-    const int q = warp & 3, ch = warp >> 2;
-    float* drow = p.dW + (size_t)(h * 128 + q * 32 + lane) * HD + ch * 128;
-#pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tDW + ((uint32_t)(q * 32) << 16) + ch * 128 + b * 32, r);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]));
     }
   }
 
@@ -602,13 +803,22 @@ pair_scatter_kernel(const float* __restrict__ drv, const float* __restrict__ t0,
 // ---------------------------------------------------------------------------------
 template <typename T, int OP, int ACT, int O, bool DO_DW>
 static int launch_bwd_inst(const BwdParams& bp, int grid, cudaStream_t st) {
-  auto kern = trunk_bwd_tc_kernel<T, OP, ACT, O, DO_DW>;
   static bool attr_done = false;
-  if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL_B));
-    attr_done = true;
+  if (DO_DW) {
+    auto kern = trunk_bwd_dw_kernel<T, OP, ACT, O>;
+    if (!attr_done) {
+      CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL_B));
+      attr_done = true;
+    }
+    kern<<<grid, DW_THREADS, SM_TOTAL_B, st>>>(bp);
+  } else {
+    auto kern = trunk_bwd_dh_kernel<T, OP, ACT, O>;
+    if (!attr_done) {
+      CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL_B));
+      attr_done = true;
+    }
+    kern<<<grid, DH_THREADS, SM_TOTAL_B, st>>>(bp);
   }
-  kern<<<grid, BWD_THREADS, SM_TOTAL_B, st>>>(bp);
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -680,11 +890,12 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   CX_LAUNCH_CHECK();
   prep_bwd_consts_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], O, net->act, S, consts);
   CX_LAUNCH_CHECK();
-  // ---------------- pass A: tiles = (outer index, 128 rows of the last axis): dW, db, dWf, d(outer features)
+  // ---------------- pass W: tiles = (outer index, 128 rows of the last axis): dW, db, dWf
+  // ---------------- pass A: same tiles: d(outer features)
   prep_inner_kernel<T><<<(unsigned)cdiv((int64_t)pl.nbA * TILE_M * HD, 256), 256, 0, st>>>(feats[C - 1], n_last, innerA, (int64_t)pl.nbA * TILE_M);
   CX_LAUNCH_CHECK();
   BwdParams a{};
-  a.w_img = w_img; a.inner_img = innerA; a.consts = consts;
+  a.w_img = w_img; a.inner_img = innerA; a.inner_f32 = feats[C - 1]; a.consts = consts;
   a.outer0 = feats[0]; a.outer1 = C == 3 ? feats[1] : nullptr; a.n_outer1 = n1;
   a.o_begin = r0 * n1; a.o_end = r1 * n1; a.n_inner = n_last; a.nb = pl.nbA;
   a.dout = dout; a.stride_o = n_last; a.stride_j = 1;
@@ -700,6 +911,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     const int64_t total = (int64_t)pl.nbA * pl.n_oA;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
     CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
+    CX_TRY((launch_bwd_t<T, false>(a, net->fusion_op, net->act, O, grid, st)));
   }
   if (C == 3) {
     pair_scatter_kernel<<<(unsigned)cdiv((r1 - r0) * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 0, dfeat[0]);
