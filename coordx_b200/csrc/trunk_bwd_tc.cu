@@ -716,7 +716,7 @@ trunk_bwd_dh_kernel(const BwdParams p) {
       const int64_t o_local = tt - jb * n_o;
       ptx::mbar_wait(B.dhfull, t & 1);
       ptx::tc_fence_after();
-      float acc = 0.f;
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};         // independent partial sums: no 128-long dependent FFMA chain
 #pragma unroll 1
       for (int b = 0; b < 4; ++b) {
         uint32_t r[32];
@@ -729,12 +729,12 @@ trunk_bwd_dh_kernel(const BwdParams p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           if (OP == COORDX_FUSE_PROD)
-            acc = fmaf(__uint_as_float(r[i]), ld_el<T>(icol + (b * 4 + (i >> 3)) * 1024 + xoff[i & 7]), acc);
+            acc4[i & 3] = fmaf(__uint_as_float(r[i]), ld_el<T>(icol + (b * 4 + (i >> 3)) * 1024 + xoff[i & 7]), acc4[i & 3]);
           else
-            acc += __uint_as_float(r[i]);
+            acc4[i & 3] += __uint_as_float(r[i]);
         }
       }
-      atomicAdd(p.d_rv + o_local * HD + k, acc);
+      atomicAdd(p.d_rv + o_local * HD + k, (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       if (OP == COORDX_FUSE_PROD) {
         __syncwarp();
         if (lane == 0) atomicAdd(const_cast<int*>(e2_done), 1);

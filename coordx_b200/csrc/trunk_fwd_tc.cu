@@ -45,9 +45,10 @@ constexpr uint32_t TILE_BYTES = NKC * CHUNK_BYTES;                  // 64 KB
 constexpr uint32_t SMEM_A = SMEM_W + NKC * CHUNK_BYTES;             // A ring
 constexpr uint32_t SMEM_PB = SMEM_A + A_STAGES * TILE_BYTES;        // float pb[256]: S b / 2pi + 6144 (polynomial sine path)
 constexpr uint32_t SMEM_PWF = SMEM_PB + HD * 4;                     // __half2 pwf[MAX_O][128]: final-layer weights as fp16 pairs
-constexpr uint32_t SMEM_XCH = SMEM_PWF + MAX_O * (HD / 2) * 4;          // float xch[2][MAX_O][128]
-constexpr uint32_t SMEM_BAR = SMEM_XCH + 2 * MAX_O * TILE_M * 4;
-constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int XCH_DEPTH = 4;
+constexpr uint32_t SMEM_XCH = SMEM_PWF + MAX_O * (HD / 2) * 4;          // float xch[XCH_DEPTH][MAX_O][128]
+constexpr uint32_t SMEM_BAR = SMEM_XCH + XCH_DEPTH * MAX_O * TILE_M * 4;
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 256 + 4 * XCH_DEPTH * 8;     // + xfull[4 quadrants][XCH_DEPTH]
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack to 1024-align the base by hand
 constexpr int NUM_THREADS = 20 * 32;
 #ifndef COORDX_FWD_MUFU_COLS
@@ -139,6 +140,7 @@ trunk_fwd_tc_kernel(const FwdParams p) {
   const uint32_t bar_empty = bar0 + 64;        // [A_STAGES]  each CTA: the MMAs reading the tile have completed (multicast commit)
   const uint32_t bar_tfull = bar0 + 128;       // [2]         each CTA: accumulator complete (multicast commit)
   const uint32_t bar_tempty = bar0 + 144;      // [2]         leader only: 16 epilogue warps (8 per CTA) have drained the accumulator
+  const uint32_t bar_xfull = bar0 + 256;       // [4][XCH_DEPTH] group 1's warp of quadrant q has deposited its partial sums (32)
   const uint32_t tmem_slot = bar0 + 160;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SMEM_BAR + 160);
 
@@ -156,6 +158,7 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         ptx::mbar_init(bar_full + 8 * s, 16);
         ptx::mbar_init(bar_empty + 8 * s, 1);
       }
+      for (int i = 0; i < 4 * XCH_DEPTH; ++i) ptx::mbar_init(bar_xfull + 8 * i, 32);
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(bar_tfull + 8 * a, 1);
         ptx::mbar_init(bar_tempty + 8 * a, 16);
@@ -340,22 +343,43 @@ trunk_fwd_tc_kernel(const FwdParams p) {
     const int e = warp >> 2;                      // column half
     const int q = warp & 3;                       // TMEM lane quadrant
     const int row = q * 32 + lane;
-    float* xch = reinterpret_cast<float*>(smem_gen + SMEM_XCH);     // [2][MAX_O][128] partial outputs of group 1
+    float* xch = reinterpret_cast<float*>(smem_gen + SMEM_XCH);     // [XCH_DEPTH][MAX_O][128] partial outputs of group 1
+    const uint32_t tempty_remote0 = ptx::mapa(bar_tempty, 0);
     // (the column half is a compile-time constant inside the body so that bias / final-layer weights stay
     //  direct constant-bank operands)
     auto run = [&](auto EC) {
     constexpr int E = decltype(EC)::value;
+    int64_t t_cur = c_begin + rank;
+    const int n_o32 = (int)n_o;
+    int jb_e = (int)(t_cur / n_o), ol_e = (int)(t_cur - (int64_t)jb_e * n_o);
+    // The two column halves of a row meet in shared memory: group 1 deposits its partial sums of tile `it` into
+    // slot it % 4 and moves on; group 0 picks them up ONE TILE LATER (after its own tile it+1), by which time they
+    // are there, so neither warp ever waits for its partner.  The asymmetry is deliberate: it keeps the two warps
+    // of an SMSP out of phase - one keeps the MUFU busy while the other does its scalar end-of-tile work
+    // (alternating the storer role balanced the groups, put them back in phase and was 9 % slower).  Slot reuse
+    // distance 4 >> the <= 1.25-tile skew the accumulator hand-off allows between any two epilogue warps.
+    float pend[O];                               // group 0: own partial sums of the previous tile
+    float* pend_dst = nullptr;
+    int pend_it = -1;
+    auto finalize = [&]() {
+      if (E == 0 && pend_it >= 0) {
+        ptx::mbar_wait(bar_xfull + 8 * (q * XCH_DEPTH + (pend_it & (XCH_DEPTH - 1))), (pend_it / XCH_DEPTH) & 1);
+        if (pend_dst != nullptr) {
+          const float* xb = xch + (pend_it & (XCH_DEPTH - 1)) * (MAX_O * TILE_M);
+#pragma unroll
+          for (int oo = 0; oo < O; ++oo) pend_dst[oo] = pend[oo] + xb[oo * TILE_M + row] + c_epi.bf[oo];
+        }
+      }
+    };
     for (int it = 0; it < n_iter; ++it) {
       const uint32_t a = it & 1, use = it >> 1;
-      const uint32_t tempty_remote = ptx::mapa(bar_tempty + 8 * a, 0);
+      const uint32_t tempty_remote = tempty_remote0 + 8 * a;
       if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 0);
       ptx::mbar_wait(bar_tfull + 8 * a, use & 1);
       if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 1);
       ptx::tc_fence_after();
-      const int64_t t = c_begin + 2 * (int64_t)it + rank;
-      const bool valid = t < c_end;
-      const int64_t jb = t / n_o;
-      const int64_t o_local = t - jb * n_o;
+      const bool valid = t_cur < c_end;
+      const int64_t jb = jb_e, o_local = ol_e;     // tile -> (inner block, outer index), advanced without divisions
       const uint32_t taddr = tmem_base + a * HD + E * (HD / 2) + ((uint32_t)(q * 32) << 16);
       // acc2: packed pair (even-column sum, odd-column sum) fed by FFMA2; acc: the polynomial path's FHFMAs
       uint64_t acc2[O];
@@ -431,15 +455,18 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         ptx::tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, rb);
         consume(ra, cb);
         ptx::tmem_ld_wait();
-        if (cb + 2 < HD / 64) ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
+        if (cb + 2 < HD / 64) {
+          ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
+        } else {
+          // the last column batch is in registers: hand the accumulator back to the tensor core now, a quarter of
+          // the tile's epilogue work early
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(tempty_remote);
+        }
         consume(rb, cb + 1);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(tempty_remote);
       if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 2);
-      // the two column halves of a row meet in shared memory: group 1 deposits, group 0 adds and stores
-      float* xb = xch + (it & 1) * (MAX_O * TILE_M);
 #pragma unroll
       for (int oo = 0; oo < O; ++oo) {
         float lo, hi;
@@ -447,17 +474,24 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         acc[oo] += lo + hi;
       }
       if (E == 1) {
+        float* xb = xch + (it & (XCH_DEPTH - 1)) * (MAX_O * TILE_M);
 #pragma unroll
         for (int oo = 0; oo < O; ++oo) xb[oo * TILE_M + row] = acc[oo];
-      }
-      ptx::named_bar_sync(2 + q, 64);          // only the two warps that share this lane quadrant (rows) meet
-      const int64_t j = jb * TILE_M + row;
-      if (E == 0 && valid && j < p.n_inner) {
-        float* dst = p.out + (o_local * p.n_inner + j) * O;
+        ptx::mbar_arrive(bar_xfull + 8 * (q * XCH_DEPTH + (it & (XCH_DEPTH - 1))));
+      } else {
+        finalize();                              // tile it - 1
+        const int64_t j = jb * TILE_M + row;
+        pend_dst = (valid && j < p.n_inner) ? p.out + (o_local * p.n_inner + j) * O : nullptr;
+        pend_it = it;
 #pragma unroll
-        for (int oo = 0; oo < O; ++oo) dst[oo] = acc[oo] + xb[oo * TILE_M + row] + c_epi.bf[oo];
+        for (int oo = 0; oo < O; ++oo) pend[oo] = acc[oo];
       }
+      if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 3);
+      t_cur += 2;
+      ol_e += 2;
+      while (ol_e >= n_o32) { ol_e -= n_o32; ++jb_e; }
     }
+    finalize();                                  // the last tile
     };
     if (e == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
   }

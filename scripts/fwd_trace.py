@@ -31,4 +31,5 @@ for it in range(8, 40):
     period = t[0, it + 1, 0] - mma[0]
     print(f'{it:3d} | {mma[1]-mma[0]:6d} {mma[2]-mma[1]:6d} {mma[3]-mma[2]:6d} | {period:6d} || {e[1]-e[0]:6d} {e[2]-e[1]:6d} (tfull@{e[1]-mma[3]:6d} after issue) || {pr[1]-pr[0]:6d} {pr[2]-pr[1]:6d}')
 per = np.diff(t[0, 8:90, 0])
+print('epi0 post (exchange+store)', (t[1, 8:90, 3] - t[1, 8:90, 2]).mean(), 'epi1 post', (t[2, 8:90, 3] - t[2, 8:90, 2]).mean(), 'epi0 loop gap', (t[1, 9:90, 0] - t[1, 8:89, 3]).mean())
 print('mean period', per.mean(), 'epi work mean', (t[1:3, 8:90, 2] - t[1:3, 8:90, 1])[(t[1:3, 8:90, 2] > 0)].mean())
