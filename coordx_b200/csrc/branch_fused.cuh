@@ -34,6 +34,12 @@ struct BranchArgs {
 
 __device__ __forceinline__ float act_exact(int act, float S, float z) { return act == COORDX_ACT_SINE ? sinf(S * z) : fmaxf(z, 0.f); }
 
+constexpr int ROWS_ = 16, WIDTH_ = 256, THREADS_ = 128;
+__device__ __noinline__ void apply_act(float* h, int act, float S, int tid) {
+#pragma unroll 1
+  for (int i = tid; i < ROWS_ * WIDTH_; i += THREADS_) h[i] = act_exact(act, S, h[i]);
+}
+
 // Thread (cg = tid % 64, rg = tid / 64) owns the 8 x 4 register tile rows 8 rg .. 8 rg + 7 x columns
 // cg, cg + 64, cg + 128, cg + 192.  W ([256 out, 256 in] row-major) is streamed in k-chunks of 16 through a
 // double-buffered, padded shared-memory tile with coalesced 64-byte row segments; per 4 k a warp issues
@@ -81,8 +87,12 @@ branch_fused_fwd_kernel(const BranchArgs a) {
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) hbuf[0][rg * 8 + r][cg + 64 * cc] = act_exact(a.act, a.S, acc[r][cc]);
+      for (int cc = 0; cc < 4; ++cc) hbuf[0][rg * 8 + r][cg + 64 * cc] = acc[r][cc];
   }
+  __syncthreads();
+  // the activation runs as a ROLLED pass over shared memory: the accurate sinf is ~60 instructions, and 32 inlined
+  // copies per layer made the kernel 160 KB of code - 40 % of its stalls were instruction-cache misses
+  apply_act(&hbuf[0][0][0], a.act, a.S, tid);
   __syncthreads();
 
   // ---- net[0 .. n_pre-1]: bias / C (modules.py:224-229); the last one without activation when fusion_before_act
@@ -148,19 +158,21 @@ branch_fused_fwd_kernel(const BranchArgs a) {
       const int j = cg + 64 * cc;
       const float bv = a.b[l][j] * a.inv_c;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float z = acc[r][cc] + bv;
-        const float y = noact ? z : act_exact(a.act, a.S, z);
-        if (last) {
-          const int64_t row = r0 + rg * 8 + r;
-          if (row < n) a.feat[c][row * WIDTH + j] = y;
-        } else {
-          hbuf[cur ^ 1][rg * 8 + r][j] = y;
-        }
-      }
+      for (int r = 0; r < 8; ++r) hbuf[cur ^ 1][rg * 8 + r][j] = acc[r][cc] + bv;
     }
     __syncthreads();
     cur ^= 1;
+    if (!noact) {
+      apply_act(&hbuf[cur][0][0], a.act, a.S, tid);
+      __syncthreads();
+    }
+    if (last) {                                   // coalesced write of the [16, 256] feature rows
+      for (int i = tid; i < ROWS * WIDTH / 4; i += THREADS) {
+        const int r = i / (WIDTH / 4);
+        if (r0 + r < n)
+          reinterpret_cast<float4*>(a.feat[c] + (r0 + r) * WIDTH)[i % (WIDTH / 4)] = reinterpret_cast<const float4*>(&hbuf[cur][r][0])[i % (WIDTH / 4)];
+      }
+    }
   }
   if (a.n_pre == 0) {                       // approx_layers = 0: the first layer's output is the feature
     for (int i = tid; i < ROWS * WIDTH; i += THREADS) {

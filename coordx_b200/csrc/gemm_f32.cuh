@@ -269,14 +269,16 @@ colsum_narrow_kernel(const float* __restrict__ dZ, int64_t total, int N, float s
   __shared__ float red[8];
   if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
   __syncthreads();
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t stride = (nthreads + N - 1) / N * N;
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float s = 0.f;
-  for (int64_t i = i0; i < total; i += stride) s += dZ[i];
-  atomicAdd(&red[i0 % N], s);
+  const int active = (256 / N) * N;               // threads per block that take part: a multiple of N
+  if ((int)threadIdx.x < active) {
+    const int64_t stride = (int64_t)gridDim.x * active;       // multiple of N: a thread's column never changes
+    const int64_t i0 = (int64_t)blockIdx.x * active + threadIdx.x;
+    float s = 0.f;
+    for (int64_t i = i0; i < total; i += stride) s += dZ[i];
+    atomicAdd(&red[i0 % N], s);
+  }
   __syncthreads();
-  if (threadIdx.x < N) atomicAdd(&db[threadIdx.x], red[threadIdx.x] * scale);
+  if ((int)threadIdx.x < N) atomicAdd(&db[threadIdx.x], red[threadIdx.x] * scale);
 }
 
 static int bias_backward(const float* dZ, int64_t ld, int M, int N, float scale, float* db, cudaStream_t st) {
