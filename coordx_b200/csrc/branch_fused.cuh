@@ -32,7 +32,7 @@ struct BranchArgs {
   const float* b[COORDX_MAX_LAYERS];
 };
 
-__device__ __forceinline__ float act_exact(int act, float S, float z) { return act == COORDX_ACT_SINE ? sinf(S * z) : fmaxf(z, 0.f); }
+__device__ __forceinline__ float act_exact(int act, float S, float z) { return act_fwd(act, S, z); }
 
 constexpr int ROWS_ = 16, WIDTH_ = 256, THREADS_ = 128;
 __device__ __noinline__ void apply_act(float* h, int act, float S, int tid) {

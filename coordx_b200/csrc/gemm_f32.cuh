@@ -159,13 +159,15 @@ static int launch_sgemm(const GemmArgs& g, cudaStream_t st) {
   GemmArgs a = g;
   // 128x128 tiles only when they still give every SM a CTA; small problems (the per-axis
   // branch layers: M = N_c <= a few thousand rows) get 4x more 64x64 CTAs instead
-  const bool big = (g.M > 64 && g.N > 64) && (EPI == EPI_ATOMIC || cdiv(g.M, 128) * cdiv(g.N, 128) >= 148);
+  // (the split-K weight-gradient GEMMs take the big tile only when their K range still yields >= 148 CTAs)
+  const bool big = (g.M > 64 && g.N > 64) &&
+                   (EPI == EPI_ATOMIC ? cdiv(g.M, 128) * cdiv(g.N, 128) * cdiv(g.K, 256) >= 148 : cdiv(g.M, 128) * cdiv(g.N, 128) >= 148);
   const int BM = big ? 128 : 64, BN = big ? 128 : 64;
   dim3 grid((unsigned)cdiv(g.N, BN), (unsigned)cdiv(g.M, BM), 1);
   if (EPI == EPI_ATOMIC) {
     // split the (long) reduction so the small [N,K] output still fills the chip
     int64_t tiles = (int64_t)grid.x * grid.y;
-    splits = (int)max((int64_t)1, min(cdiv(g.K, 256), cdiv(148 * 4, tiles)));
+    splits = (int)max((int64_t)1, min(cdiv(g.K, big ? 256 : 128), cdiv(148 * 4, tiles)));
     a.kchunk = (int)(cdiv(cdiv(g.K, splits), 8) * 8);
     splits = (int)cdiv(g.K, a.kchunk);
     grid.z = splits;
