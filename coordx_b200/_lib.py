@@ -71,6 +71,7 @@ SIGNATURES = {
     'coordx_profile_enable': (C.c_int, [C.c_int]),
     'coordx_profile_last_ms': (C.c_int, [C.POINTER(C.c_float)]),
     'coordx_profile_set_trace': (C.c_int, [C.c_void_p]),
+    'coordx_profile_set_bwd_trace': (C.c_int, [C.c_void_p, C.c_int]),
     'coordx_trunk_tc_supported': (C.c_int, [C.POINTER(Net), C.c_int]),
     'coordx_branch_workspace_bytes': (C.c_size_t, [C.POINTER(Net), C.c_int, C.c_int64, C.c_int]),
     'coordx_branch_forward': (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,

@@ -184,6 +184,11 @@ int coordx_profile_set_trace(void* dev_buf) {
   tc::profile_set_trace(dev_buf);
   return 0;
 }
+// same for the backward trunk kernels; pass: 0 = dW pass, 1 = dH pass (outer axes), 2 = dH pass (last axis)
+int coordx_profile_set_bwd_trace(void* dev_buf, int pass) {
+  tc::profile_set_bwd_trace(dev_buf, pass);
+  return 0;
+}
 
 // milliseconds of the last profiled trunk kernel (synchronises on its end event)
 int coordx_profile_last_ms(float* ms_host) {

@@ -22,6 +22,9 @@ struct Pack<__nv_bfloat16> {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  static __device__ __forceinline__ float unpack(uint32_t v, int hi) {       // element 0 (low) or 1 (high) as fp32
+    return __uint_as_float(hi ? (v & 0xffff0000u) : (v << 16));
+  }
 };
 template <>
 struct Pack<__half> {
@@ -30,6 +33,10 @@ struct Pack<__half> {
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float unpack(uint32_t v, int hi) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&v);
+    return hi ? __high2float(h) : __low2float(h);
   }
 };
 
@@ -59,6 +66,7 @@ int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int
                      int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 void profile_enable(bool on);
 void profile_set_trace(void* dev_buf);
+void profile_set_bwd_trace(void* dev_buf, int pass);
 int profile_last_ms(float* ms_host);
 
 size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1);

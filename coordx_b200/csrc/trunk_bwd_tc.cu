@@ -89,6 +89,8 @@ struct BwdParams {
   const uint8_t* w_img;      // full W image of the forward prep: 4 K-chunks of [256 rows x 128 B]
   const uint8_t* inner_img;  // inner axis table, per 128-row block 4 K-chunks [128 x 128 B]   (dH pass)
   const float* inner_f32;    // the same table as fp32 [n_inner, 256]                           (dW pass)
+  const float* w_f32;        // trunk weight [256 n_out, 256 k_in] fp32                          (dH pass, E2)
+  long long* trace;          // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
   const float* consts;       // [256] bias' then [MAX_O][256] wfs (see prep_bwd_consts_kernel)
   const float* outer0;
   const float* outer1;
@@ -152,6 +154,11 @@ __device__ __forceinline__ void unpack8<__half>(const uint4& q, float (&f)[8]) {
 }
 
 
+constexpr int TRACE_ITERS = 96;
+__device__ __forceinline__ void trace_stamp(const BwdParams& p, int role, int it, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_ITERS) p.trace[(role * TRACE_ITERS + it) * 4 + slot] = clock64();
+}
+
 // barrier block (byte offsets from SM_BAR), shared by the two kernels
 struct Bars {
   uint32_t full, empty;      // [4] H chunk (dH pass) / [2] H stage (dW pass)
@@ -190,78 +197,69 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
   uint8_t* dzrow = smem_gen + sm_dz + hh * CH;                  // 64 points = one 128-byte row of this chunk
   for (int t = 0; t < my_tiles; ++t) {
     const uint32_t zb = t & 1, zuse = t >> 1;
+    if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 0);
     ptx::mbar_wait(B.dsfull, t & 1);
     ptx::mbar_wait(B.zfull + 8 * zb, zuse & 1);
+    if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 1);
     ptx::tc_fence_after();
-#pragma unroll 1
-    for (int b = 0; b < 2; ++b) {
-      // d0[i] = dout[p_i, 0]  (O == 1)   |   g[i] = sum_o dout[p_i, o] * wfs[o][n]  (O > 1)
-      float g[32];
-      if (O == 1) {
+    // The whole dZ^T row of this thread (64 points = 32 packed registers) is computed BEFORE the wait for the
+    // shared-memory tile: the tensor core is still reading dZ(t-1) (G3 / G2 of the previous tile) while this
+    // tile's sin/cos run; only the 8 stores at the end need the tile.  (With the wait in front of the first store
+    // E1 and the second GEMM strictly alternated: 5.4 k clk per tile, profiles/r01c_bwd_dh_timeline.txt.)
+    uint32_t pk[32];
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {                        // warp-uniform shared-memory addresses: broadcast LDS.128
-          const float4 d4 = *reinterpret_cast<const float4*>(ds + b * 32 + i4 * 4);
-          g[i4 * 4 + 0] = d4.x; g[i4 * 4 + 1] = d4.y; g[i4 * 4 + 2] = d4.z; g[i4 * 4 + 3] = d4.w;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float* dp = ds + (b * 32 + i) * O;
-          float acc = 0.f;
-#pragma unroll
-          for (int oo = 0; oo < O; ++oo) acc = fmaf(dp[oo], wfs_n[oo], acc);
-          g[i] = acc;
-        }
-      }
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_z0 + zb * 128 + ((uint32_t)(q * 32) << 16) + hh * 64 + b * 32, r);
+    for (int b = 0; b < 4; ++b) {                  // 16 columns (points) per TMEM load
+      uint32_t r[16];
+      ptx::tmem_ld_32x32b_x16(tmem_z0 + zb * 128 + ((uint32_t)(q * 32) << 16) + hh * 64 + b * 16, r);
       ptx::tmem_ld_wait();
-      if (b == 1) {                                // every Z^T column of this warp is in registers
+      if (b == 3) {                                // every Z^T column of this warp is in registers
         ptx::tc_fence_before();
         ptx::mbar_arrive(B.zempty + 8 * zb);
       }
-      float dzv[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float z = __uint_as_float(r[i]);
-        const float gw = O == 1 ? g[i] * wfs_n[0] : g[i];
-        float av;                                  // activation value (for dWf); the derivative is folded into dzv
-        if (ACT == COORDX_ACT_SINE) {
-          const float th = fmaf(z, p.S, bias_n);
-          dzv[i] = gw * __cosf(th);
-          av = DO_DW ? __sinf(th) : 0.f;
-        } else {
-          const float pre = z + bias_n;
-          dzv[i] = pre > 0.f ? gw : 0.f;
-          av = fmaxf(pre, 0.f);
-        }
-        if (DO_DW) {
-          db_acc += dzv[i];
+      for (int e2 = 0; e2 < 8; ++e2) {
+        float dz2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = e2 * 2 + u;
+          const float* dp = ds + (b * 16 + i) * O;              // warp-uniform shared-memory address: broadcast
+          float gw;
           if (O == 1) {
-            dwf_acc[0] = fmaf(g[i], av, dwf_acc[0]);
+            gw = dp[0] * wfs_n[0];
           } else {
-            const float* dp = ds + (b * 32 + i) * O;
+            gw = 0.f;
+#pragma unroll
+            for (int oo = 0; oo < O; ++oo) gw = fmaf(dp[oo], wfs_n[oo], gw);
+          }
+          const float z = __uint_as_float(r[i]);
+          float av;                                // activation value (for dWf); the derivative is folded into dz
+          if (ACT == COORDX_ACT_SINE) {
+            const float th = fmaf(z, p.S, bias_n);
+            dz2[u] = gw * __cosf(th);
+            av = DO_DW ? __sinf(th) : 0.f;
+          } else {
+            const float pre = z + bias_n;
+            dz2[u] = pre > 0.f ? gw : 0.f;
+            av = fmaxf(pre, 0.f);
+          }
+          if (DO_DW) {
+            db_acc += dz2[u];
 #pragma unroll
             for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
           }
         }
-      }
-      if (b == 1 && (DO_DW && O > 1 ? false : true)) ptx::mbar_arrive(B.dsempty);   // last read of the staged dout
-      // points 32b .. 32b+31 of row n -> 4 swizzled 16-byte pieces (the tensor core must be done with dZ(t-1))
-      if (b == 0) ptx::mbar_wait(B.dzempty, (t & 1) ^ 1);
-#pragma unroll
-      for (int pc = 0; pc < 4; ++pc) {
-        uint4 w;
-        w.x = Pack<T>::pack(dzv[pc * 8 + 0], dzv[pc * 8 + 1]);
-        w.y = Pack<T>::pack(dzv[pc * 8 + 2], dzv[pc * 8 + 3]);
-        w.z = Pack<T>::pack(dzv[pc * 8 + 4], dzv[pc * 8 + 5]);
-        w.w = Pack<T>::pack(dzv[pc * 8 + 6], dzv[pc * 8 + 7]);
-        *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, b * 32 + pc * 8)) = w;
+        pk[b * 8 + e2] = Pack<T>::pack(dz2[0], dz2[1]);
       }
     }
-    if (DO_DW && O > 1) ptx::mbar_arrive(B.dsempty);
+    ptx::mbar_arrive(B.dsempty);                   // last read of the staged dout
+    ptx::mbar_wait(B.dzempty, (t & 1) ^ 1);        // the tensor core is done with dZ(t-1)
+    if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 2);
+#pragma unroll
+    for (int pc = 0; pc < 8; ++pc)                 // 8 points = one swizzled 16-byte piece of row n
+      *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, pc * 8)) = make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
     ptx::fence_proxy_async();
     ptx::mbar_arrive(B.dzfull + 8 * hh);
+    if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 3);
   }
   if (DO_DW && my_tiles > 0) {
     atomicAdd(p.db + h * 128 + row, db_acc);
@@ -596,22 +594,43 @@ trunk_bwd_dh_kernel(const BwdParams p) {
         ptx::mma_commit(B.zfull + 8 * zb);
       };
       auto issue_g2 = [&](int t) {
+        trace_stamp(p, 0, t, 0);
         ptx::mbar_wait(B.dzfull, t & 1);
         ptx::mbar_wait(B.dzfull + 8, t & 1);
+        trace_stamp(p, 0, t, 1);
         ptx::mbar_wait(B.dhempty, (t & 1) ^ 1);
+        trace_stamp(p, 0, t, 2);
         ptx::tc_fence_after();
-        // dH^T[k_in, pts] = W_h^T dZ^T, two M-blocks of 128 input features; K = 128 n_out = 16 tile rows per step
+        if (OP == COORDX_FUSE_PROD) {
+          // d rowvec(o)[k] = sum_p inner[p,k] sum_n dZ[p,n] W[n,k] = sum_n W[n,k] M^T[k,n] with M^T = inner^T dZ:
+          // the tensor core contracts over the POINTS (A = inner block, MN-major, two M-blocks of 128 input
+          // features; B = dZ^T tile, K-major; K = 128 points = 16 tile rows per step) and E2 is left with a dot
+          // product against W[:,k], which is constant for the whole kernel and lives in its registers
+          constexpr uint32_t id_g2p = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 0);
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
+          for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_W + blk * 2 * CH + ks * 2048, CH);
-            const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_DZ_DH + ks * 2048, CH);
-            ptx::mma_f16_ss(tDH + blk * 128, a, b, id_g2, ks != 0);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_INNER + blk * 2 * CH + ks * 2048, CH);
+              const uint64_t b = ptx::umma_desc_k_sw128(smem_base + SM_DZ_DH + (ks >> 2) * CH + (ks & 3) * 32);
+              ptx::mma_f16_ss(tDH + blk * 128, a, b, id_g2p, ks != 0);
+            }
+          }
+        } else {
+          // dH^T[k_in, pts] = W_h^T dZ^T, two M-blocks of 128 input features; K = 128 n_out = 16 tile rows per step
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SM_W + blk * 2 * CH + ks * 2048, CH);
+              const uint64_t b = ptx::umma_desc_mn_sw128(smem_base + SM_DZ_DH + ks * 2048, CH);
+              ptx::mma_f16_ss(tDH + blk * 128, a, b, id_g2, ks != 0);
+            }
           }
         }
         ptx::mma_commit(B.dhfull);
         ptx::mma_commit(B.dzempty);
+        trace_stamp(p, 0, t, 3);
       };
       issue_g1(0);
       for (int t = 0; t < my_tiles; ++t) {
@@ -636,21 +655,44 @@ trunk_bwd_dh_kernel(const BwdParams p) {
       const int64_t tt = t_begin + t;
       const int64_t jb = tt / n_o;
       const int64_t o_local = tt - jb * n_o;
-#pragma unroll
-      for (int kc = 0; kc < NKC; ++kc) {
-        float4 x0, x1;
-        load_rowvec8<OP>(p, p.o_begin + o_local, kc * KCHUNK + g8 * 8, x0, x1);
-        rv[kc][0] = Pack<T>::pack(x0.x, x0.y);
-        rv[kc][1] = Pack<T>::pack(x0.z, x0.w);
-        rv[kc][2] = Pack<T>::pack(x1.x, x1.y);
-        rv[kc][3] = Pack<T>::pack(x1.z, x1.w);
-      }
-      float dreg[O];
       {
-        const int64_t j = jb * TILE_M + ptid;
+        // all 8 (16 with a second outer axis) loads are issued back to back: one L2 round trip per tile, not four
+        // (the branch on outer1 inside a per-chunk helper serialised them: 2.9 k clk of the producer's 5.3 k period)
+        const int64_t o = p.o_begin + o_local;
+        int64_t i0 = o, i1 = 0;
+        if (p.outer1) { i0 = o / p.n_outer1; i1 = o - i0 * p.n_outer1; }
+        const float4* s0 = reinterpret_cast<const float4*>(p.outer0 + i0 * HD + g8 * 8);
+        float4 xa[NKC], xb[NKC];
 #pragma unroll
-        for (int oo = 0; oo < O; ++oo)
-          dreg[oo] = j < p.n_inner ? __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo) : 0.f;
+        for (int kc = 0; kc < NKC; ++kc) { xa[kc] = __ldg(s0 + kc * (KCHUNK / 4)); xb[kc] = __ldg(s0 + kc * (KCHUNK / 4) + 1); }
+        if (p.outer1) {
+          const float4* s1 = reinterpret_cast<const float4*>(p.outer1 + i1 * HD + g8 * 8);
+#pragma unroll
+          for (int kc = 0; kc < NKC; ++kc) {
+            const float4 ya = __ldg(s1 + kc * (KCHUNK / 4)), yb = __ldg(s1 + kc * (KCHUNK / 4) + 1);
+            if (OP == COORDX_FUSE_PROD) {
+              xa[kc].x *= ya.x; xa[kc].y *= ya.y; xa[kc].z *= ya.z; xa[kc].w *= ya.w;
+              xb[kc].x *= yb.x; xb[kc].y *= yb.y; xb[kc].z *= yb.z; xb[kc].w *= yb.w;
+            } else {
+              xa[kc].x += ya.x; xa[kc].y += ya.y; xa[kc].z += ya.z; xa[kc].w += ya.w;
+              xb[kc].x += yb.x; xb[kc].y += yb.y; xb[kc].z += yb.z; xb[kc].w += yb.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          rv[kc][0] = Pack<T>::pack(xa[kc].x, xa[kc].y);
+          rv[kc][1] = Pack<T>::pack(xa[kc].z, xa[kc].w);
+          rv[kc][2] = Pack<T>::pack(xb[kc].x, xb[kc].y);
+          rv[kc][3] = Pack<T>::pack(xb[kc].z, xb[kc].w);
+        }
+      }
+      if (t + 1 < my_tiles) {                      // next tile's rowvec -> L1 while this tile is produced
+        const int64_t tn = tt + 1, jn = tn / n_o;
+        const int64_t on = p.o_begin + (tn - jn * n_o);
+        const int64_t i0n = p.outer1 ? on / p.n_outer1 : on;
+        ptx::prefetch_l1(p.outer0 + i0n * HD + ptid * 2);          // 128 threads x 8 B cover the 1 KB row
+        if (p.outer1) ptx::prefetch_l1(p.outer1 + (on - i0n * p.n_outer1) * HD + ptid * 2);
       }
       if (jb != cur_jb) {
         ptx::named_bar_sync(1, 128);
@@ -668,9 +710,12 @@ trunk_bwd_dh_kernel(const BwdParams p) {
         inner_phase ^= 1;
         cur_jb = jb;
       }
+      if (ptid == 0) trace_stamp(p, 3, t, 0);
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_wait(B.empty + 8 * kc, (t & 1) ^ 1);
+      if (ptid == 0) trace_stamp(p, 3, t, 1);
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
-        ptx::mbar_wait(B.empty + 8 * kc, (t & 1) ^ 1);
         const uint8_t* src = smem_gen + SM_INNER + kc * CH + piece_off;
         uint8_t* dst = smem_gen + SM_H + kc * CH + piece_off;
         uint4 v[8];
@@ -685,8 +730,19 @@ trunk_bwd_dh_kernel(const BwdParams p) {
           w.w = fuse2<T, OP>(v[i].w, rv[kc][3]);
           *reinterpret_cast<uint4*>(dst + i * 2048) = w;
         }
-        ptx::fence_proxy_async();
-        ptx::mbar_arrive(B.full + 8 * kc);
+      }
+      // ONE generic->async proxy fence per tile (a fence per chunk cost ~4 x 200 clk of MEMBAR), and no global load
+      // of this thread is outstanding while it runs (dout is fetched after it)
+      ptx::fence_proxy_async();
+#pragma unroll
+      for (int kc = 0; kc < NKC; ++kc) ptx::mbar_arrive(B.full + 8 * kc);
+      if (ptid == 0) trace_stamp(p, 3, t, 2);
+      float dreg[O];
+      {
+        const int64_t j = jb * TILE_M + ptid;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo)
+          dreg[oo] = j < p.n_inner ? __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo) : 0.f;
       }
       ptx::mbar_wait(B.dsempty, (t & 1) ^ 1);      // E1(t-1) has read its dout
       {
@@ -695,50 +751,72 @@ trunk_bwd_dh_kernel(const BwdParams p) {
         for (int oo = 0; oo < O; ++oo) ds[oo] = dreg[oo];
       }
       ptx::mbar_arrive(B.dsfull);
+      if (ptid == 0) trace_stamp(p, 3, t, 3);
     }
   } else if (warp < W_E2) {
+    if (OP == COORDX_FUSE_PROD) ptx::setmaxnreg_dec<72>();       // hand 8 x 256 registers to E2 (W column in registers)
     e1_stage<T, ACT, O, false>(p, B, smem_gen, tZ, SM_DZ_DH, h, warp, lane, my_tiles);
   } else {
+    if (OP == COORDX_FUSE_PROD) ptx::setmaxnreg_inc<88>();
     // ============================ E2: dH^T -> d rowvec ============================
     // dH is produced transposed too (lanes = input feature k): d rowvec(o)[k] = sum_p dH^T[k,p] * inner[p,k] is a
     // per-thread sum over the 128 point columns - one atomic per thread per tile, no shuffles.
     // warp (q, blk): k = 128 blk + 32 q + lane
     const int q = warp & 3, blk = (warp - W_E2) >> 2;
     const int k = blk * 128 + q * 32 + lane;
-    // inner[p][k] inside the swizzled block: chunk k / 64, row p, piece ((k % 64) / 8) ^ (p % 8), element k % 8
-    const uint8_t* icol = smem_gen + SM_INNER + (k >> 6) * CH + (k & 7) * 2;
-    uint32_t xoff[8];
+    // prod: W[128 h + n][k] for the 128 output features of this CTA, 16-bit pairs (n = 2i, 2i+1): 64 registers
+    uint32_t wreg[64];
+    if (OP == COORDX_FUSE_PROD) {
+      uint32_t chain = 0;                          // batches of 8 loads chained through an opaque zero (bounds the loads in flight)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) xoff[r] = (uint32_t)(r * 128) + (uint32_t)(((((k & 63) >> 3) ^ r) & 7) << 4);
+      for (int i4 = 0; i4 < 64; i4 += 4) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(p.w_f32 + (size_t)(h * 128 + 2 * i4 + u) * HD + k + chain);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wreg[i4 + u] = Pack<T>::pack(v[2 * u], v[2 * u + 1]);
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(wreg[i4 + 3]));
+      }
+    }
+    // (no 64-bit division inside the loop: it is a call, and the 64 live W registers would be spilled around it)
+    int o_local = my_tiles > 0 ? (int)(t_begin - (t_begin / n_o) * n_o) : 0;
+    const int n_o32 = (int)n_o;
     for (int t = 0; t < my_tiles; ++t) {
-      const int64_t tt = t_begin + t;
-      const int64_t jb = tt / n_o;
-      const int64_t o_local = tt - jb * n_o;
+      if (warp == W_E2 && lane == 0) trace_stamp(p, 2, t, 0);
       ptx::mbar_wait(B.dhfull, t & 1);
+      if (warp == W_E2 && lane == 0) trace_stamp(p, 2, t, 1);
       ptx::tc_fence_after();
       float acc4[4] = {0.f, 0.f, 0.f, 0.f};         // independent partial sums: no 128-long dependent FFMA chain
-#pragma unroll 1
-      for (int b = 0; b < 4; ++b) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tDH + blk * 128 + ((uint32_t)(q * 32) << 16) + b * 32, r);
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {                // 8 columns per load: (prod) n = 8 b .. 8 b + 7, (sum) points
+        uint32_t r[8];
+        ptx::tmem_ld_32x32b_x8(tDH + blk * 128 + ((uint32_t)(q * 32) << 16) + b * 8, r);
         ptx::tmem_ld_wait();
-        if (b == 3) {
+        if (b == 15) {
           ptx::tc_fence_before();
           ptx::mbar_arrive(B.dhempty);
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (OP == COORDX_FUSE_PROD)
-            acc4[i & 3] = fmaf(__uint_as_float(r[i]), ld_el<T>(icol + (b * 4 + (i >> 3)) * 1024 + xoff[i & 7]), acc4[i & 3]);
-          else
+        for (int i = 0; i < 8; ++i) {
+          if (OP == COORDX_FUSE_PROD) {
+            // opaque to the optimiser on purpose: the unpack is loop-invariant and would otherwise be hoisted out of
+            // the tile loop as 128 fp32 registers (spilled)
+            uint32_t wp = wreg[b * 4 + (i >> 1)];
+            asm volatile("" : "+r"(wp));
+            const float w = Pack<T>::unpack(wp, i & 1);
+            acc4[i & 3] = fmaf(__uint_as_float(r[i]), w, acc4[i & 3]);
+          } else {
             acc4[i & 3] += __uint_as_float(r[i]);
+          }
         }
       }
-      atomicAdd(p.d_rv + o_local * HD + k, (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
       if (OP == COORDX_FUSE_PROD) {
         __syncwarp();
         if (lane == 0) atomicAdd(const_cast<int*>(e2_done), 1);
       }
+      if (warp == W_E2 && lane == 0) trace_stamp(p, 2, t, 2);
+      if (++o_local == n_o32) o_local = 0;
     }
   }
 
@@ -843,6 +921,9 @@ static int launch_bwd_t(const BwdParams& bp, int op, int act, int O, int grid, c
                                 : launch_bwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU, DO_DW>(bp, O, grid, st);
 }
 
+static long long* g_bwd_trace = nullptr;
+static int g_bwd_trace_pass = 1;      // 0 = dW pass, 1 = dH pass A, 2 = dH pass B
+
 struct BwdPlan {
   size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, total;
   int nbA, nbB;
@@ -895,7 +976,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   prep_inner_kernel<T><<<(unsigned)cdiv((int64_t)pl.nbA * TILE_M * HD, 256), 256, 0, st>>>(feats[C - 1], n_last, innerA, (int64_t)pl.nbA * TILE_M);
   CX_LAUNCH_CHECK();
   BwdParams a{};
-  a.w_img = w_img; a.inner_img = innerA; a.inner_f32 = feats[C - 1]; a.consts = consts;
+  a.w_img = w_img; a.inner_img = innerA; a.inner_f32 = feats[C - 1]; a.w_f32 = net->layer_w[L]; a.consts = consts;
   a.outer0 = feats[0]; a.outer1 = C == 3 ? feats[1] : nullptr; a.n_outer1 = n1;
   a.o_begin = r0 * n1; a.o_end = r1 * n1; a.n_inner = n_last; a.nb = pl.nbA;
   a.dout = dout; a.stride_o = n_last; a.stride_j = 1;
@@ -910,7 +991,9 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   {
     const int64_t total = (int64_t)pl.nbA * pl.n_oA;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
+    a.trace = g_bwd_trace_pass == 0 ? g_bwd_trace : nullptr;
     CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
+    a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
     CX_TRY((launch_bwd_t<T, false>(a, net->fusion_op, net->act, O, grid, st)));
   }
   if (C == 3) {
@@ -926,7 +1009,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     prep_inner_kernel<T><<<(unsigned)cdiv((int64_t)pl.nbB * TILE_M * HD, 256), 256, 0, st>>>(feats[0] + r0 * HD, pl.n_innerB, innerB, (int64_t)pl.nbB * TILE_M);
   CX_LAUNCH_CHECK();
   BwdParams b{};
-  b.w_img = w_img; b.inner_img = innerB; b.consts = consts;
+  b.w_img = w_img; b.inner_img = innerB; b.w_f32 = net->layer_w[L]; b.consts = consts;
   b.outer0 = feats[C - 1]; b.outer1 = nullptr; b.n_outer1 = 1;
   b.o_begin = 0; b.o_end = n_last; b.n_inner = pl.n_innerB; b.nb = pl.nbB;
   b.dout = dout; b.stride_o = 1; b.stride_j = n_last;
@@ -945,6 +1028,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
 
 namespace coordx {
 namespace tc {
+void profile_set_bwd_trace(void* dev_buf, int pass) { tcb::g_bwd_trace = (long long*)dev_buf; tcb::g_bwd_trace_pass = pass; }
 size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1) { return tcb::plan_bwd(net, n, r0, r1).total; }
 int trunk_backward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
                       const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws,

@@ -94,6 +94,7 @@ int coordx_profile_enable(int on);
 int coordx_profile_last_ms(float* ms_host);
 /* optional pipeline timeline of the forward trunk kernel: device buffer of 4*96*4 int64 (see profiles/), NULL = off */
 int coordx_profile_set_trace(void* dev_buf);
+int coordx_profile_set_bwd_trace(void* dev_buf, int pass);   /* backward kernels: pass 0 = dW, 1 = dH */
 /* 1 if the tcgen05 trunk kernels cover this architecture at `precision`. */
 int coordx_trunk_tc_supported(const coordx_net* net, int precision);
 
