@@ -216,6 +216,11 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
         ptx::tc_fence_before();
         ptx::mbar_arrive(B.zempty + 8 * zb);
       }
+      float4 d4[4];                                // O == 1: dout of the batch's 16 points, 4 broadcast LDS.128
+      if (O == 1) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) d4[v] = *reinterpret_cast<const float4*>(ds + b * 16 + v * 4);
+      }
 #pragma unroll
       for (int e2 = 0; e2 < 8; ++e2) {
         float dz2[2];
@@ -223,9 +228,11 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
         for (int u = 0; u < 2; ++u) {
           const int i = e2 * 2 + u;
           const float* dp = ds + (b * 16 + i) * O;              // warp-uniform shared-memory address: broadcast
-          float gw;
+          float gw, d0 = 0.f;
           if (O == 1) {
-            gw = dp[0] * wfs_n[0];
+            const float4 dv = d4[i >> 2];
+            d0 = (i & 3) == 0 ? dv.x : ((i & 3) == 1 ? dv.y : ((i & 3) == 2 ? dv.z : dv.w));
+            gw = d0 * wfs_n[0];
           } else {
             gw = 0.f;
 #pragma unroll
@@ -244,8 +251,12 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
           }
           if (DO_DW) {
             db_acc += dz2[u];
+            if (O == 1) {
+              dwf_acc[0] = fmaf(d0, av, dwf_acc[0]);
+            } else {
 #pragma unroll
-            for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
+              for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
+            }
           }
         }
         pk[b * 8 + e2] = Pack<T>::pack(dz2[0], dz2[1]);
