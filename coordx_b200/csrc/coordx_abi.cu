@@ -269,9 +269,14 @@ size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int
 int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
                          int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, void* stream) {
   CX_TRY(check_net(net));
-  if (!feats || !n || !out) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (!feats || !n) return set_err(COORDX_ERR_ARG, "null argument%s");
   if (row_begin < 0 || row_end > n[0] || row_begin > row_end) return set_err(COORDX_ERR_ARG, "bad slab%s [%lld, %lld)", "", row_begin, row_end);
-  if (row_begin == row_end) return 0;
+  {                                                        // empty grid (an axis without samples): nothing to do
+    int64_t pts = row_end - row_begin;
+    for (int c = 1; c < net->n_branches; ++c) pts *= n[c];
+    if (pts == 0) return 0;
+  }
+  if (!out) return set_err(COORDX_ERR_ARG, "null argument%s");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
@@ -306,9 +311,14 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
                           int64_t row_end, const float* dout, coordx_grads* grads, float* const* dfeat, int precision,
                           void* ws, size_t ws_bytes, void* stream) {
   CX_TRY(check_net(net));
-  if (!feats || !n || !dout || !grads || !dfeat) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (!feats || !n || !grads || !dfeat) return set_err(COORDX_ERR_ARG, "null argument%s");
   if (row_begin < 0 || row_end > n[0] || row_begin > row_end) return set_err(COORDX_ERR_ARG, "bad slab%s [%lld, %lld)", "", row_begin, row_end);
-  if (row_begin == row_end) return 0;
+  {
+    int64_t pts = row_end - row_begin;
+    for (int c = 1; c < net->n_branches; ++c) pts *= n[c];
+    if (pts == 0) return 0;
+  }
+  if (!dout) return set_err(COORDX_ERR_ARG, "null argument%s");
   cudaStream_t st = (cudaStream_t)stream;
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
