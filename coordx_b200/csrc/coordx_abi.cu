@@ -4,6 +4,7 @@
 #include "elementwise.cuh"
 #include "gemm_f32.cuh"
 #include "branch_fused.cuh"
+#include "sum_sep.cuh"
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -250,6 +251,8 @@ int coordx_branch_backward(const coordx_net* net, int branch, const float* coord
 size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t row_begin, int64_t row_end,
                                     int precision, int backward) {
   if (check_net(net) != 0 || !n) return 0;
+  if (sep::enabled() && sep::supported(net) && (!backward || sep::backward_fits(net, n, row_begin, row_end)))
+    return sep::workspace_bytes(net, n, row_begin, row_end, backward != 0);
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return 0;
     if (backward) return tc::bwd_workspace_bytes(net, n, row_begin, row_end) + 1024;
@@ -278,6 +281,8 @@ int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const
   }
   if (!out) return set_err(COORDX_ERR_ARG, "null argument%s");
   cudaStream_t st = (cudaStream_t)stream;
+  // sum-fused sine trunk: separable evaluation over the per-axis tables, exact to fp32 rounding, any precision
+  if (sep::enabled() && sep::supported(net)) return sep::forward(net, feats, n, row_begin, row_end, out, ws, ws_bytes, st);
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
     return tc::trunk_forward_tc(net, feats, n, row_begin, row_end, out, precision, ws, ws_bytes, st);
@@ -320,6 +325,8 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
   }
   if (!dout) return set_err(COORDX_ERR_ARG, "null argument%s");
   cudaStream_t st = (cudaStream_t)stream;
+  if (sep::enabled() && sep::supported(net) && sep::backward_fits(net, n, row_begin, row_end))
+    return sep::backward(net, feats, n, row_begin, row_end, dout, grads, dfeat, ws, ws_bytes, st);
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
     const int Lf = net->n_layers - 1;

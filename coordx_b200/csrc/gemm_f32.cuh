@@ -26,6 +26,8 @@ struct GemmArgs {
   const float* Zprev;   // EPI_DX: multiply by act'(Zprev[m,n]) when non-null
   int64_t ldz;
   int kchunk;           // EPI_ATOMIC: K range per blockIdx.z
+  int64_t sa;           // element stride of A along its contiguous index (0 = 1): an interleaved channel of [.., O]
+  int64_t cs;           // EPI_LINEAR: column stride of Y / Z (0 = 1): writes one channel of an interleaved [.., O]
 };
 
 // AK : A(m,k) = A[m*lda + k]  (k contiguous)   else A[k*lda + m]
@@ -49,6 +51,7 @@ sgemm_kernel(GemmArgs g) {
     if (kbeg >= kend) return;
   }
 
+  const int64_t sa = g.sa ? g.sa : 1, cs = g.cs ? g.cs : 1;
   constexpr int LA = (BM * BK + NT - 1) / NT, LB = (BN * BK + NT - 1) / NT;
   float ra[LA], rb[LB];
 
@@ -60,7 +63,7 @@ sgemm_kernel(GemmArgs g) {
       if (AK) { r = e / BK; kk = e % BK; } else { kk = e / BM; r = e % BM; }
       int m = m0 + r, k = k0 + kk;
       float v = 0.f;
-      if (e < BM * BK && m < g.M && k < kend) v = AK ? g.A[(int64_t)m * g.lda + k] : g.A[(int64_t)k * g.lda + m];
+      if (e < BM * BK && m < g.M && k < kend) v = AK ? g.A[(int64_t)m * g.lda + k * sa] : g.A[(int64_t)k * g.lda + m * sa];
       ra[i] = v;
     }
 #pragma unroll
@@ -140,8 +143,8 @@ sgemm_kernel(GemmArgs g) {
       float v = acc[i][j];
       if (EPI == EPI_LINEAR) {
         if (g.bias) v += g.bias[n] * g.bscale;
-        if (g.Z) g.Z[(int64_t)m * g.ldc + n] = v;
-        if (g.Y) g.Y[(int64_t)m * g.ldc + n] = g.act < 0 ? v : act_fwd(g.act, g.S, v);
+        if (g.Z) g.Z[(int64_t)m * g.ldc + n * cs] = v;
+        if (g.Y) g.Y[(int64_t)m * g.ldc + n * cs] = g.act < 0 ? v : act_fwd(g.act, g.S, v);
       } else if (EPI == EPI_DX) {
         if (g.Zprev) v *= act_grad(g.act, g.S, g.Zprev[(int64_t)m * g.ldz + n]);
         g.Y[(int64_t)m * g.ldc + n] = v;

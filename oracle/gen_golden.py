@@ -7,6 +7,7 @@ fixtures to tests/golden/.  The fixtures travel to the GPU box; this script and
 /root/reference do not need to.
 
     python oracle/gen_golden.py            # (re)writes tests/golden/*.npz
+    python oracle/gen_golden.py NAME ...   # only the named cases (seeds depend on the position in CASES)
 
 Each fixture holds: cfg (json), the reference state_dict, per-axis coords, gt,
 model_out of SingleBVPNet.forward({'coords_split': ...}) (modules.py:447-454),
@@ -80,6 +81,9 @@ CASES = [
     ('img_sine_sum_h256', dict(type='sine', out_features=1, hidden_features=256, fusion_operator='sum'), (40, 130), 'mse', 'linspace'),
     ('occ_sine_prod_h256', dict(type='sine', in_features=3, out_features=1, hidden_features=256, fusion_operator='prod'), (6, 10, 150), 'bce', 'rand'),
     ('img_relu_prod_h256', dict(type='relu', out_features=1, hidden_features=256, fusion_operator='prod'), (30, 128), 'mse', 'rand'),
+    # sum-fused sine nets with three axes / a 2-D axis and RGB output (the separable trunk path)
+    ('occ_sine_sum_h64', dict(type='sine', in_features=3, out_features=1, hidden_features=64, fusion_operator='sum'), (9, 10, 11), 'bce', 'rand'),
+    ('video_st_sine_sum_h256', dict(type='sine', in_features=3, out_features=3, hidden_features=256, split_rule=[1, 2], fusion_operator='sum'), (12, 150), 'mse', 'rand'),
 ]
 
 
@@ -175,7 +179,10 @@ def run_case(name, kw, shape, loss_kind, mode, seed):
 if __name__ == '__main__':
     import io
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])                              # optional: names of the cases to (re)generate
     for i, (name, kw, shape, loss_kind, mode) in enumerate(CASES):
+        if only and name not in only:
+            continue
         real, sys.stdout = sys.stdout, io.StringIO()      # the reference ctor prints the module tree
         try:
             run_case(name, kw, shape, loss_kind, mode, seed=100 + i)
