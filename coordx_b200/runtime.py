@@ -93,3 +93,79 @@ def infer_grid_host(model: 'M.SingleBVPNet', coords_host: Sequence[torch.Tensor]
         _lib.check(lib.coordx_infer_grid_host(desc.net, c_arr, n_arr, out_host.data_ptr(), prec, ws.data_ptr(),
                                               ws.numel(), torch.cuda.current_stream().cuda_stream), 'coordx_infer_grid_host')
     return out_host
+
+
+class CapturedTrainStep:
+    """CUDA-graph replay of ONE training iteration of training.py:112-146 for fixed shapes:
+    model({'coords_split': ...}) -> loss -> backward -> [clip_grad_norm_ 1.0] -> Adam.step, i.e. the body of the
+    reference's epoch loop without its TensorBoard / .item() synchronisations.  A step is one graph launch instead
+    of ~130 Python-driven launches: the small named shapes (256x256 image, 32^3 occupancy batches) are otherwise
+    bound by launch overhead, not by the GPU.
+
+    coords: the 'coords_split' list ([1, N_0, 1, .., f_0], ...); gt: [1, P, O].  loss: 'mse' (loss_functions.py:8-12),
+    'bce' (:56-60) or a callable(model_out, gt) -> scalar.  `replay()` returns the static loss tensor (device);
+    `set_batch()` overwrites the static inputs in place.  The warm-up iterations needed before capture are undone:
+    parameters and optimizer state are restored to their values at construction."""
+
+    def __init__(self, model: 'M.SingleBVPNet', coords: Sequence[torch.Tensor], gt: torch.Tensor, loss='mse',
+                 lr: float = 1e-4, clip_grad: bool = False, optimizer: torch.optim.Optimizer = None, warmup: int = 3):
+        self.model = model
+        self.static_coords = [c.detach().clone() for c in coords]
+        self.static_gt = gt.detach().clone()
+        self.clip_grad = clip_grad
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.opt = optimizer or torch.optim.Adam(self.params, lr=lr, capturable=True)
+        if not all(g.get('capturable', False) for g in self.opt.param_groups):
+            raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
+        if callable(loss):
+            self.loss_fn = loss
+        elif loss == 'mse':
+            self.loss_fn = lambda out, gt_: ((out - gt_) ** 2).mean()
+        elif loss == 'bce':
+            self.loss_fn = lambda out, gt_: torch.nn.functional.binary_cross_entropy_with_logits(out, gt_)
+        else:
+            raise ValueError(f'unknown loss {loss!r}')
+        saved_p = [p.detach().clone() for p in self.params]
+        saved_s = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()}
+                   for p in self.params}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self.opt.zero_grad(set_to_none=True)
+                self._iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._iteration()
+        with torch.no_grad():                                    # undo the warm-up updates
+            for p, s in zip(self.params, saved_p):
+                p.copy_(s)
+            for p in self.params:
+                st, old = self.opt.state.get(p, {}), saved_s[id(p)]
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.copy_(old[k]) if k in old else v.zero_()
+        torch.cuda.synchronize()
+
+    def _iteration(self):
+        out = self.model({'coords_split': self.static_coords})['model_out']
+        loss = self.loss_fn(out, self.static_gt)
+        loss.backward()
+        if self.clip_grad:
+            torch.nn.utils.clip_grad_norm_(self.params, max_norm=1.)
+        self.opt.step()
+        return loss
+
+    def set_batch(self, coords: Sequence[torch.Tensor] = None, gt: torch.Tensor = None) -> None:
+        if coords is not None:
+            for s, c in zip(self.static_coords, coords):
+                s.copy_(c, non_blocking=True)
+        if gt is not None:
+            self.static_gt.copy_(gt, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.static_loss
