@@ -29,6 +29,8 @@
 //
 // CTA = 21 warps: 0-7 E1 (quadrant = warp % 4, point half = warp / 4) | 8-15 E2 (quadrant, column half) |
 // 16-19 producers | 20 MMA issuer.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -91,6 +93,7 @@ struct BwdParams {
   const float* inner_f32;    // the same table as fp32 [n_inner, 256]                           (dW pass)
   const float* w_f32;        // trunk weight [256 n_out, 256 k_in] fp32                          (dH pass, E2)
   long long* trace;          // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
+  uint8_t* dz_img;           // optional: dZ^T_h tiles, 32 KB per (tile, h), written by the dW pass and read by the drv pass
   const float* consts;       // [256] bias' then [MAX_O][256] wfs (see prep_bwd_consts_kernel)
   const float* outer0;
   const float* outer1;
@@ -343,7 +346,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         ptx::mbar_init(B.zempty + 8 * c, 256);
         ptx::mbar_init(B.dzfull + 8 * c, 128);
       }
-      ptx::mbar_init(B.dzempty, 1);
+      ptx::mbar_init(B.dzempty, p.dz_img ? 2 : 1);  // tensor-core commit (+ the bulk store has read the tile)
       ptx::mbar_init(B.dsfull, 128);
       ptx::mbar_init(B.dsempty, 256);
       ptx::mbar_init(B.w, 1);
@@ -388,6 +391,8 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         for (int c = 0; c < 2; ++c) {              // K = 128 points, 16 per step; starts on the first 64-point chunk of dZ^T
           ptx::mbar_wait(B.dzfull + 8 * c, t & 1);
           ptx::tc_fence_after();
+          // keep the dZ^T tile for the d-rowvec pass: it then needs neither G1 nor E1 nor an H tile
+          if (p.dz_img) ptx::bulk_s2g(p.dz_img + ((size_t)(t_begin + t) * 2 + h) * (2 * CH) + c * CH, smem_base + SM_DZ_DW + c * CH, CH);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int ks = c * 4 + k;
@@ -397,6 +402,11 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         }
         ptx::mma_commit(B.empty + 8 * (t & 1));    // H stage free for the producers
         ptx::mma_commit(B.dzempty);                // dZ^T tile free for E1
+        if (p.dz_img) {
+          ptx::bulk_commit_group();
+          ptx::bulk_wait_group_read0();            // (the copy engine reads 32 KB while G3 runs)
+          ptx::mbar_arrive(B.dzempty);
+        }
       };
       // G1(t+1) is issued AHEAD of G3(t): E1 is the longest stage, so its input must never queue behind G3 in the
       // in-order tensor pipe (polling "whichever is ready first" was measured 18 % slower for exactly that reason)
@@ -406,6 +416,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         issue_g3(t);
       }
       ptx::mma_commit(B.dwfull);
+      if (p.dz_img) ptx::bulk_wait_group0();
     }
     __syncwarp();
   } else if (warp >= W_PROD) {
@@ -839,6 +850,185 @@ trunk_bwd_dh_kernel(const BwdParams p) {
   }
 }
 
+// =================================================================================
+// d-rowvec pass from STORED dZ^T tiles (same tiling as the dW pass, which wrote them):
+//   G2' M^T = inner^T dZ (prod) | dH^T = W_h^T dZ^T (sum)  ->  E2 d rowvec(o)
+// No G1, no E1, no H tile: the copy engine streams the 32 KB tiles (4-deep ring), the accumulator is double-buffered
+// in TMEM (2 x 256 columns), E2 is the only arithmetic.  64 KB of global reads per point tile: HBM-bound.
+// CTA = 10 warps: 0-7 E2 | 8 tile loader | 9 MMA issuer.
+// =================================================================================
+constexpr int DRV_THREADS = 10 * 32, DRV_STAGES = 4;
+constexpr uint32_t SMR_OPER = 0;                        // inner block (prod) / W_h (sum): 4 chunks
+constexpr uint32_t SMR_DZ = 4 * CH;                     // DRV_STAGES x 2 chunks
+constexpr uint32_t SMR_BAR = SMR_DZ + DRV_STAGES * 2 * CH;
+constexpr uint32_t SMR_TOTAL = SMR_BAR + 256;
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(DRV_THREADS, 1)
+trunk_bwd_drv_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_base + SMR_BAR;
+  const uint32_t b_dzfull = bar0, b_dzempty = bar0 + 8 * DRV_STAGES, b_dhfull = bar0 + 16 * DRV_STAGES, b_dhempty = b_dhfull + 16,
+                 b_oper = b_dhfull + 32, b_slot = b_dhfull + 40;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SMR_BAR + 16 * DRV_STAGES + 40);
+  constexpr int W_LOAD = 8, W_MMA = 9;
+
+  const int h = blockIdx.x & 1;
+  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int64_t t_begin = total * cta / n_cta;
+  const int64_t t_end = total * (cta + 1) / n_cta;
+  const int my_tiles = (int)(t_end - t_begin);
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < DRV_STAGES; ++s) {
+        ptx::mbar_init(b_dzfull + 8 * s, 1);
+        ptx::mbar_init(b_dzempty + 8 * s, 1);
+      }
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(b_dhfull + 8 * c, 1);
+        ptx::mbar_init(b_dhempty + 8 * c, 256);
+      }
+      ptx::mbar_init(b_oper, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(b_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == W_LOAD) {
+    // ============================ loader: operand block + the ring of dZ^T tiles ============================
+    if (lane == 0) {
+      int64_t cur_jb = -1;
+      uint32_t oper_loads = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int64_t tt = t_begin + t;
+        const int64_t jb = tt / n_o;
+        if (OP == COORDX_FUSE_PROD ? jb != cur_jb : t == 0) {
+          // the previous tile's MMAs read the operand block: its commit on the ring's "empty" barrier covers them
+          if (t > 0) ptx::mbar_wait(b_dzempty + 8 * ((t - 1) % DRV_STAGES), ((t - 1) / DRV_STAGES) & 1);
+          ptx::mbar_arrive_expect_tx(b_oper, 4 * CH);
+          for (int kc = 0; kc < 4; ++kc) {
+            if (OP == COORDX_FUSE_PROD)
+              ptx::bulk_g2s(smem_base + SMR_OPER + kc * CH, p.inner_img + (size_t)jb * INNER_BYTES + (size_t)kc * CH, CH, b_oper);
+            else
+              ptx::bulk_g2s(smem_base + SMR_OPER + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, b_oper);
+          }
+          ++oper_loads;
+          cur_jb = jb;
+        }
+        const int s = t % DRV_STAGES;
+        ptx::mbar_wait(b_dzempty + 8 * s, ((t / DRV_STAGES) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(b_dzfull + 8 * s, 2 * CH);
+        ptx::bulk_g2s(smem_base + SMR_DZ + s * 2 * CH, p.dz_img + ((size_t)tt * 2 + h) * (2 * CH), 2 * CH, b_dzfull + 8 * s);
+      }
+      (void)oper_loads;
+    }
+    __syncwarp();
+  } else if (warp == W_MMA) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t id_g2 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 1);    // sum: A = W_h^T MN-major, B = dZ^T MN-major
+      constexpr uint32_t id_g2p = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 0);   // prod: A = inner^T MN-major, B = dZ^T K-major
+      int64_t cur_jb = -1;
+      uint32_t oper_phase = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int64_t jb = (t_begin + t) / n_o;
+        if (OP == COORDX_FUSE_PROD ? jb != cur_jb : t == 0) {
+          ptx::mbar_wait(b_oper, oper_phase);
+          oper_phase ^= 1;
+          cur_jb = jb;
+        }
+        const int s = t % DRV_STAGES, ab = t & 1;
+        ptx::mbar_wait(b_dzfull + 8 * s, (t / DRV_STAGES) & 1);
+        ptx::mbar_wait(b_dhempty + 8 * ab, ((t >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t dz = smem_base + SMR_DZ + s * 2 * CH;
+        const uint32_t acc = tmem_base + ab * 256;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SMR_OPER + blk * 2 * CH + ks * 2048, CH);
+            if (OP == COORDX_FUSE_PROD)
+              ptx::mma_f16_ss(acc + blk * 128, a, ptx::umma_desc_k_sw128(dz + (ks >> 2) * CH + (ks & 3) * 32), id_g2p, ks != 0);
+            else
+              ptx::mma_f16_ss(acc + blk * 128, a, ptx::umma_desc_mn_sw128(dz + ks * 2048, CH), id_g2, ks != 0);
+          }
+        }
+        ptx::mma_commit(b_dhfull + 8 * ab);
+        ptx::mma_commit(b_dzempty + 8 * s);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ E2: accumulator -> d rowvec (as in the dH kernel) ============================
+    const int q = warp & 3, blk = warp >> 2;
+    const int k = blk * 128 + q * 32 + lane;
+    uint32_t wreg[64];
+    if (OP == COORDX_FUSE_PROD) {
+      uint32_t chain = 0;
+#pragma unroll
+      for (int i4 = 0; i4 < 64; i4 += 4) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(p.w_f32 + (size_t)(h * 128 + 2 * i4 + u) * HD + k + chain);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wreg[i4 + u] = Pack<T>::pack(v[2 * u], v[2 * u + 1]);
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(wreg[i4 + 3]));
+      }
+    }
+    int o_local = my_tiles > 0 ? (int)(t_begin - (t_begin / n_o) * n_o) : 0;
+    const int n_o32 = (int)n_o;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int ab = t & 1;
+      ptx::mbar_wait(b_dhfull + 8 * ab, (t >> 1) & 1);
+      ptx::tc_fence_after();
+      float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        uint32_t r[8];
+        ptx::tmem_ld_32x32b_x8(tmem_base + ab * 256 + blk * 128 + ((uint32_t)(q * 32) << 16) + b * 8, r);
+        ptx::tmem_ld_wait();
+        if (b == 15) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(b_dhempty + 8 * ab);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (OP == COORDX_FUSE_PROD) {
+            uint32_t wp = wreg[b * 4 + (i >> 1)];
+            asm volatile("" : "+r"(wp));             // keep the unpack inside the loop (see the dH kernel)
+            acc4[i & 3] = fmaf(__uint_as_float(r[i]), Pack<T>::unpack(wp, i & 1), acc4[i & 3]);
+          } else {
+            acc4[i & 3] += __uint_as_float(r[i]);
+          }
+        }
+      }
+      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      if (++o_local == n_o32) o_local = 0;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // small helpers for the 3-axis case
 // ---------------------------------------------------------------------------------
@@ -932,11 +1122,38 @@ static int launch_bwd_t(const BwdParams& bp, int op, int act, int O, int grid, c
                                 : launch_bwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU, DO_DW>(bp, O, grid, st);
 }
 
+template <typename T>
+static int launch_drv(const BwdParams& bp, int op, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_drv_kernel<T, COORDX_FUSE_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMR_TOTAL));
+    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_drv_kernel<T, COORDX_FUSE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMR_TOTAL));
+    attr_done = true;
+  }
+  if (op == COORDX_FUSE_PROD)
+    trunk_bwd_drv_kernel<T, COORDX_FUSE_PROD><<<grid, DRV_THREADS, SMR_TOTAL, st>>>(bp);
+  else
+    trunk_bwd_drv_kernel<T, COORDX_FUSE_SUM><<<grid, DRV_THREADS, SMR_TOTAL, st>>>(bp);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+// dZ^T tiles kept between the dW pass and the d-rowvec pass (64 KB per 128-point tile): on unless
+// COORDX_BWD_DZ_REUSE=0 or the tiles would need more than COORDX_BWD_DZ_MAX_GB (default 24) of workspace
+static bool dz_reuse(int64_t tiles) {
+  const char* e = getenv("COORDX_BWD_DZ_REUSE");
+  if (e && e[0] == '0') return false;
+  const char* m = getenv("COORDX_BWD_DZ_MAX_GB");
+  const double max_gb = m ? atof(m) : 24.0;
+  return (double)tiles * (4.0 * CH) <= max_gb * 1e9;
+}
+
 static long long* g_bwd_trace = nullptr;
 static int g_bwd_trace_pass = 1;      // 0 = dW pass, 1 = dH pass A, 2 = dH pass B
 
 struct BwdPlan {
-  size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, total;
+  size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, dz_off, total;
+  bool reuse;
   int nbA, nbB;
   int64_t n_innerA, n_innerB, n_oA;
 };
@@ -956,6 +1173,8 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   pl.innerA_off = off; off += (size_t)pl.nbA * INNER_BYTES;
   pl.innerB_off = off; off += (size_t)pl.nbB * INNER_BYTES;
   pl.drv_off = off; off += C == 3 ? align_up((size_t)pl.n_oA * HD * 4, 1024) : 0;
+  pl.reuse = dz_reuse((int64_t)pl.nbA * pl.n_oA);
+  pl.dz_off = off; off += pl.reuse ? (size_t)pl.nbA * pl.n_oA * (4 * CH) : 0;
   pl.total = off;
   return pl;
 }
@@ -1003,9 +1222,13 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     const int64_t total = (int64_t)pl.nbA * pl.n_oA;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
     a.trace = g_bwd_trace_pass == 0 ? g_bwd_trace : nullptr;
+    a.dz_img = pl.reuse ? base + pl.dz_off : nullptr;
     CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
     a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
-    CX_TRY((launch_bwd_t<T, false>(a, net->fusion_op, net->act, O, grid, st)));
+    if (pl.reuse)
+      CX_TRY((launch_drv<T>(a, net->fusion_op, grid, st)));
+    else
+      CX_TRY((launch_bwd_t<T, false>(a, net->fusion_op, net->act, O, grid, st)));
   }
   if (C == 3) {
     pair_scatter_kernel<<<(unsigned)cdiv((r1 - r0) * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 0, dfeat[0]);
