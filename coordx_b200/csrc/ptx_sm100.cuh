@@ -63,6 +63,16 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// one lane of a fully converged warp.  Code under `if (elect_one())` is known to the compiler to run on a single
+// lane, so warp-uniform operands of tcgen05.mma / commit reach their uniform registers with a plain R2UR; under
+// `if (lane == 0)` every MMA is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~20 instructions, ~140 clk
+// per MMA: slower than a 64-clk M128xN128xK16 MMA executes).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -75,6 +75,14 @@ prep_inner_kernel(const float* __restrict__ feat, int64_t n, uint8_t* __restrict
 }
 
 
+// fp32 table [n, 256] -> 16-bit rows, natural order (rowvec source of the dH-pass producers)
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_rows16_kernel(const float* __restrict__ feat, int64_t n, uint8_t* __restrict__ img) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx < n * HD) reinterpret_cast<T*>(img)[idx] = to_T<T>(feat[idx]);
+}
+
 constexpr uint32_t CH = 16384;                    // one [128 rows x 128 B] SWIZZLE_128B chunk
 constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB): this CTA's 128 output features of W
 // dH pass:  H 4 chunks | dZ^T 2 chunks | inner block 4 chunks          dW pass:  H stage 0 | H stage 1 | dZ^T 2 chunks
@@ -84,6 +92,7 @@ constexpr uint32_t SM_H1 = 8 * CH, SM_DZ_DW = 12 * CH;
 constexpr uint32_t SM_BAR = 14 * CH;
 constexpr uint32_t SM_DOUT = SM_BAR + 256;        // float dout[128 points][MAX_O] of the current tile (staged by the producers)
 constexpr uint32_t SM_TOTAL_B = SM_DOUT + TILE_M * MAX_O * 4;     // 231680 bytes <= 227 KB
+constexpr uint32_t SM_RV = SM_DOUT + 1024;        // O <= 2: two 512-byte rowvec slots in the unused tail of the dout staging area
 // dH pass: 0-7 E1 | 8-15 E2 | 16-19 producers | 20 MMA.   dW pass: 0-7 E1 | 8-15 producers | 16 MMA.
 constexpr int DH_THREADS = 21 * 32, DW_THREADS = 17 * 32;
 
@@ -93,6 +102,9 @@ struct BwdParams {
   const float* inner_f32;    // the same table as fp32 [n_inner, 256]                           (dW pass)
   const float* w_f32;        // trunk weight [256 n_out, 256 k_in] fp32                          (dH pass, E2)
   long long* trace;          // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
+  int dbg;
+  const uint8_t* outer_img;  // optional: the outer0 table as 16-bit rows [n, 256] (512 B each): dH-pass producers fetch rowvec(o) with
+                             // the copy engine two tiles ahead instead of global loads on their critical path (outer1 == nullptr only)
   uint8_t* dz_img;           // optional: dZ^T_h tiles, 32 KB per (tile, h), written by the dW pass and read by the drv pass
   const float* consts;       // [256] bias' then [MAX_O][256] wfs (see prep_bwd_consts_kernel)
   const float* outer0;
@@ -171,10 +183,11 @@ struct Bars {
   uint32_t dhfull, dhempty;  // dH accumulator (dH pass)
   uint32_t dsfull, dsempty;  // dout staging
   uint32_t w, inner, dwfull, tmem_slot, e2_done;
+  uint32_t rv;               // [2] rowvec ring (dH pass, copy engine)
   __device__ explicit Bars(uint32_t b0)
       : full(b0), empty(b0 + 32), zfull(b0 + 64), zempty(b0 + 80), dzfull(b0 + 96), dzempty(b0 + 112), dhfull(b0 + 120),
         dhempty(b0 + 128), dsfull(b0 + 136), dsempty(b0 + 144), w(b0 + 152), inner(b0 + 160), dwfull(b0 + 168),
-        tmem_slot(b0 + 176), e2_done(b0 + 184) {}
+        tmem_slot(b0 + 176), e2_done(b0 + 184), rv(b0 + 192) {}
 };
 
 // ---------------------------------------------------------------------------------
@@ -365,7 +378,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
 
   if (warp == W_MMA) {
     // ============================ MMA issuer ============================
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one()) {       // (elect, not lane == 0: see ptx::elect_one)
       ptx::mbar_arrive_expect_tx(B.w, 4 * CH);
       for (int kc = 0; kc < 4; ++kc)
         ptx::bulk_g2s(smem_base + SM_W + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, B.w);
@@ -577,6 +590,8 @@ trunk_bwd_dh_kernel(const BwdParams p) {
       ptx::mbar_init(B.dsempty, 256);
       ptx::mbar_init(B.w, 1);
       ptx::mbar_init(B.inner, 1);
+      ptx::mbar_init(B.rv, 1);
+      ptx::mbar_init(B.rv + 8, 1);
       *e2_done = 0;
       ptx::fence_mbar_init();
     }
@@ -592,7 +607,7 @@ trunk_bwd_dh_kernel(const BwdParams p) {
 
   if (warp == W_MMA) {
     // ============================ MMA issuer ============================
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one()) {       // (elect, not lane == 0: see ptx::elect_one)
       ptx::mbar_arrive_expect_tx(B.w, 4 * CH);
       for (int kc = 0; kc < 4; ++kc)
         ptx::bulk_g2s(smem_base + SM_W + kc * CH, p.w_img + (size_t)kc * W_CHUNK_BYTES + (size_t)h * CH, CH, B.w);
@@ -607,6 +622,7 @@ trunk_bwd_dh_kernel(const BwdParams p) {
         for (int kc = 0; kc < 4; ++kc) {
           ptx::mbar_wait(B.full + 8 * kc, t & 1);
           ptx::tc_fence_after();
+          if (!(p.dbg & 16))
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(tZ + zb * 128, ptx::umma_desc_k_sw128(smem_base + SM_W + kc * CH + k * 32),
@@ -629,6 +645,7 @@ trunk_bwd_dh_kernel(const BwdParams p) {
           // features; B = dZ^T tile, K-major; K = 128 points = 16 tile rows per step) and E2 is left with a dot
           // product against W[:,k], which is constant for the whole kernel and lives in its registers
           constexpr uint32_t id_g2p = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 0);
+          if (!(p.dbg & 32))
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
@@ -673,11 +690,46 @@ trunk_bwd_dh_kernel(const BwdParams p) {
     uint32_t inner_phase = 0;
     int64_t cur_jb = -1;
     uint32_t rv[NKC][4];
+    // rowvec(o) through the copy engine, two tiles ahead (16-bit rows of p.outer_img): a global load here sat on the
+    // producers' critical path for ~2.3 k clk per tile (the LSU queue is full of this role's own LDS/STS traffic)
+    const bool rv_tma = O <= 2 && p.outer_img != nullptr && p.outer1 == nullptr;
+    const int n_o32 = (int)n_o;
+    int64_t jb = my_tiles > 0 ? t_begin / n_o : 0;                       // (no 64-bit division inside the loop)
+    int o_local = my_tiles > 0 ? (int)(t_begin - jb * n_o) : 0;
+    if (rv_tma && ptid == 0) {
+      int on = o_local;
+      for (int u = 0; u < 2 && u < my_tiles; ++u) {
+        ptx::mbar_arrive_expect_tx(B.rv + 8 * u, 512);
+        ptx::bulk_g2s(smem_base + SM_RV + u * 512, p.outer_img + (size_t)(p.o_begin + on) * 512, 512, B.rv + 8 * u);
+        if (++on == n_o32) on = 0;
+      }
+    }
     for (int t = 0; t < my_tiles; ++t) {
-      const int64_t tt = t_begin + t;
-      const int64_t jb = tt / n_o;
-      const int64_t o_local = tt - jb * n_o;
+      if (t > 0 && ++o_local == n_o32) { o_local = 0; ++jb; }
+      float dreg[O];                               // dout of this thread's point: issued first, consumed after the H tile is written
       {
+        const int64_t j = jb * TILE_M + ptid;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo)
+          dreg[oo] = j < p.n_inner ? __ldg(p.dout + ((int64_t)o_local * p.stride_o + j * p.stride_j) * O + oo) : 0.f;
+      }
+      if (rv_tma) {
+        ptx::mbar_wait(B.rv + 8 * (t & 1), (t >> 1) & 1);
+        const uint4* src = reinterpret_cast<const uint4*>(smem_gen + SM_RV + (t & 1) * 512 + g8 * 16);
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+          const uint4 v = src[kc * 8];
+          rv[kc][0] = v.x; rv[kc][1] = v.y; rv[kc][2] = v.z; rv[kc][3] = v.w;
+        }
+        ptx::named_bar_sync(2, 128);               // every producer has read the slot
+        if (ptid == 0 && t + 2 < my_tiles) {
+          int on = o_local + 2;
+          if (on >= n_o32) on -= n_o32;
+          if (on >= n_o32) on -= n_o32;            // n_o == 1
+          ptx::mbar_arrive_expect_tx(B.rv + 8 * (t & 1), 512);
+          ptx::bulk_g2s(smem_base + SM_RV + (t & 1) * 512, p.outer_img + (size_t)(p.o_begin + on) * 512, 512, B.rv + 8 * (t & 1));
+        }
+      } else {
         // all 8 (16 with a second outer axis) loads are issued back to back: one L2 round trip per tile, not four
         // (the branch on outer1 inside a per-chunk helper serialised them: 2.9 k clk of the producer's 5.3 k period)
         const int64_t o = p.o_begin + o_local;
@@ -708,13 +760,14 @@ trunk_bwd_dh_kernel(const BwdParams p) {
           rv[kc][2] = Pack<T>::pack(xb[kc].x, xb[kc].y);
           rv[kc][3] = Pack<T>::pack(xb[kc].z, xb[kc].w);
         }
-      }
-      if (t + 1 < my_tiles) {                      // next tile's rowvec -> L1 while this tile is produced
-        const int64_t tn = tt + 1, jn = tn / n_o;
-        const int64_t on = p.o_begin + (tn - jn * n_o);
-        const int64_t i0n = p.outer1 ? on / p.n_outer1 : on;
-        ptx::prefetch_l1(p.outer0 + i0n * HD + ptid * 2);          // 128 threads x 8 B cover the 1 KB row
-        if (p.outer1) ptx::prefetch_l1(p.outer1 + (on - i0n * p.n_outer1) * HD + ptid * 2);
+        if (t + 1 < my_tiles) {                    // next tile's rowvec -> L1 while this tile is produced
+          int on32 = o_local + 1;
+          if (on32 == n_o32) on32 = 0;
+          const int64_t on = p.o_begin + on32;
+          const int64_t i0n = p.outer1 ? on / p.n_outer1 : on;
+          ptx::prefetch_l1(p.outer0 + i0n * HD + ptid * 2);          // 128 threads x 8 B cover the 1 KB row
+          if (p.outer1) ptx::prefetch_l1(p.outer1 + (on - i0n * p.n_outer1) * HD + ptid * 2);
+        }
       }
       if (jb != cur_jb) {
         ptx::named_bar_sync(1, 128);
@@ -759,13 +812,6 @@ trunk_bwd_dh_kernel(const BwdParams p) {
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) ptx::mbar_arrive(B.full + 8 * kc);
       if (ptid == 0) trace_stamp(p, 3, t, 2);
-      float dreg[O];
-      {
-        const int64_t j = jb * TILE_M + ptid;
-#pragma unroll
-        for (int oo = 0; oo < O; ++oo)
-          dreg[oo] = j < p.n_inner ? __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo) : 0.f;
-      }
       ptx::mbar_wait(B.dsempty, (t & 1) ^ 1);      // E1(t-1) has read its dout
       {
         float* ds = reinterpret_cast<float*>(smem_gen + SM_DOUT) + ptid * O;
@@ -930,6 +976,7 @@ trunk_bwd_drv_kernel(const BwdParams p) {
         }
         const int s = t % DRV_STAGES;
         ptx::mbar_wait(b_dzempty + 8 * s, ((t / DRV_STAGES) & 1) ^ 1);
+        if ((p.dbg & 1) && t >= DRV_STAGES) { ptx::mbar_arrive(b_dzfull + 8 * s); continue; }
         ptx::mbar_arrive_expect_tx(b_dzfull + 8 * s, 2 * CH);
         ptx::bulk_g2s(smem_base + SMR_DZ + s * 2 * CH, p.dz_img + ((size_t)tt * 2 + h) * (2 * CH), 2 * CH, b_dzfull + 8 * s);
       }
@@ -938,7 +985,7 @@ trunk_bwd_drv_kernel(const BwdParams p) {
     __syncwarp();
   } else if (warp == W_MMA) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t id_g2 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 1);    // sum: A = W_h^T MN-major, B = dZ^T MN-major
       constexpr uint32_t id_g2p = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 0);   // prod: A = inner^T MN-major, B = dZ^T K-major
       int64_t cur_jb = -1;
@@ -956,12 +1003,16 @@ trunk_bwd_drv_kernel(const BwdParams p) {
         ptx::tc_fence_after();
         const uint32_t dz = smem_base + SMR_DZ + s * 2 * CH;
         const uint32_t acc = tmem_base + ab * 256;
+        if (!(p.dbg & 2))
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SMR_OPER + blk * 2 * CH + ks * 2048, CH);
-            if (OP == COORDX_FUSE_PROD)
+            if (p.dbg & 4)     // TIMING EXPERIMENT ONLY: K-major A over the same bytes
+              ptx::mma_f16_ss(acc + blk * 128, ptx::umma_desc_k_sw128(smem_base + SMR_OPER + blk * 2 * CH + (ks >> 2) * CH + (ks & 3) * 32),
+                              ptx::umma_desc_k_sw128(dz + (ks >> 2) * CH + (ks & 3) * 32), ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 0), ks != 0);
+            else if (OP == COORDX_FUSE_PROD)
               ptx::mma_f16_ss(acc + blk * 128, a, ptx::umma_desc_k_sw128(dz + (ks >> 2) * CH + (ks & 3) * 32), id_g2p, ks != 0);
             else
               ptx::mma_f16_ss(acc + blk * 128, a, ptx::umma_desc_mn_sw128(dz + ks * 2048, CH), id_g2, ks != 0);
@@ -996,19 +1047,25 @@ trunk_bwd_drv_kernel(const BwdParams p) {
       ptx::mbar_wait(b_dhfull + 8 * ab, (t >> 1) & 1);
       ptx::tc_fence_after();
       float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+      // 4 loads of 32 columns, double-buffered: a load per 8 columns with its own wait made E2 latency-bound
+      // (16 serialised TMEM round trips = 2.3 k clk per tile for 1 k clk of tensor work)
+      const uint32_t tacc = tmem_base + ab * 256 + blk * 128 + ((uint32_t)(q * 32) << 16);
+      uint32_t ra[32], rb[32];
+      if (p.dbg & 8) { ptx::tc_fence_before(); ptx::mbar_arrive(b_dhempty + 8 * ab); continue; }
+      ptx::tmem_ld_32x32b_x32(tacc, ra);
 #pragma unroll
-      for (int b = 0; b < 16; ++b) {
-        uint32_t r[8];
-        ptx::tmem_ld_32x32b_x8(tmem_base + ab * 256 + blk * 128 + ((uint32_t)(q * 32) << 16) + b * 8, r);
+      for (int b = 0; b < 4; ++b) {
+        uint32_t(&r)[32] = (b & 1) ? rb : ra;
         ptx::tmem_ld_wait();
-        if (b == 15) {
+        if (b < 3) ptx::tmem_ld_32x32b_x32(tacc + (b + 1) * 32, (b & 1) ? ra : rb);
+        if (b == 3) {
           ptx::tc_fence_before();
           ptx::mbar_arrive(b_dhempty + 8 * ab);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 32; ++i) {
           if (OP == COORDX_FUSE_PROD) {
-            uint32_t wp = wreg[b * 4 + (i >> 1)];
+            uint32_t wp = wreg[b * 16 + (i >> 1)];
             asm volatile("" : "+r"(wp));             // keep the unpack inside the loop (see the dH kernel)
             acc4[i & 3] = fmaf(__uint_as_float(r[i]), Pack<T>::unpack(wp, i & 1), acc4[i & 3]);
           } else {
@@ -1152,7 +1209,7 @@ static long long* g_bwd_trace = nullptr;
 static int g_bwd_trace_pass = 1;      // 0 = dW pass, 1 = dH pass A, 2 = dH pass B
 
 struct BwdPlan {
-  size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, dz_off, total;
+  size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, rows_off, dz_off, total;
   bool reuse;
   int nbA, nbB;
   int64_t n_innerA, n_innerB, n_oA;
@@ -1173,6 +1230,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   pl.innerA_off = off; off += (size_t)pl.nbA * INNER_BYTES;
   pl.innerB_off = off; off += (size_t)pl.nbB * INNER_BYTES;
   pl.drv_off = off; off += C == 3 ? align_up((size_t)pl.n_oA * HD * 4, 1024) : 0;
+  pl.rows_off = off; off += align_up((size_t)pl.n_innerA * HD * 2, 1024);      // 16-bit rows of the last axis (pass B rowvec)
   pl.reuse = dz_reuse((int64_t)pl.nbA * pl.n_oA);
   pl.dz_off = off; off += pl.reuse ? (size_t)pl.nbA * pl.n_oA * (4 * CH) : 0;
   pl.total = off;
@@ -1223,6 +1281,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
     a.trace = g_bwd_trace_pass == 0 ? g_bwd_trace : nullptr;
     a.dz_img = pl.reuse ? base + pl.dz_off : nullptr;
+    a.dbg = getenv("COORDX_DBG") ? atoi(getenv("COORDX_DBG")) : 0;
     CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
     a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
     if (pl.reuse)
@@ -1242,13 +1301,18 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   else
     prep_inner_kernel<T><<<(unsigned)cdiv((int64_t)pl.nbB * TILE_M * HD, 256), 256, 0, st>>>(feats[0] + r0 * HD, pl.n_innerB, innerB, (int64_t)pl.nbB * TILE_M);
   CX_LAUNCH_CHECK();
+  prep_rows16_kernel<T><<<(unsigned)cdiv(n_last * HD, 256), 256, 0, st>>>(feats[C - 1], n_last, base + pl.rows_off);
+  CX_LAUNCH_CHECK();
   BwdParams b{};
+  b.outer_img = base + pl.rows_off;
   b.w_img = w_img; b.inner_img = innerB; b.w_f32 = net->layer_w[L]; b.consts = consts;
   b.outer0 = feats[C - 1]; b.outer1 = nullptr; b.n_outer1 = 1;
   b.o_begin = 0; b.o_end = n_last; b.n_inner = pl.n_innerB; b.nb = pl.nbB;
   b.dout = dout; b.stride_o = 1; b.stride_j = n_last;
   b.d_rv = dfeat[C - 1];
   b.S = S;
+  b.trace = g_bwd_trace_pass == 2 ? g_bwd_trace : nullptr;
+  b.dbg = getenv("COORDX_DBG") ? atoi(getenv("COORDX_DBG")) : 0;
   {
     const int64_t total = (int64_t)pl.nbB * n_last;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);

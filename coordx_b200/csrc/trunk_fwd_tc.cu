@@ -205,7 +205,7 @@ trunk_fwd_tc_kernel(const FwdParams p) {
 
   if (warp >= 16) {
     ptx::setmaxnreg_dec<REGS_MMA>();
-    if (warp == 16 && rank == 0 && lane == 0 && n_iter > 0) {
+    if (warp == 16 && rank == 0 && n_iter > 0 && ptx::elect_one()) {     // (elect, not lane == 0: see ptx::elect_one)
       // ============================ MMA issuer (leader CTA, one thread) ============================
       constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 2 * TILE_M, HD);
       for (int it = 0; it < n_iter; ++it) {

@@ -20,7 +20,8 @@ def step():
     ((out - gt) ** 2).mean().backward()
 for _ in range(2):
     step()
-lib.coordx_profile_set_bwd_trace(tr.data_ptr(), 1)
+PASS = int(os.environ.get('TRACE_PASS', '2'))      # 0 = dW pass, 2 = dH pass (last axis); pass 1 streams stored tiles (no stamps)
+lib.coordx_profile_set_bwd_trace(tr.data_ptr(), PASS)
 step()
 torch.cuda.synchronize()
 lib.coordx_profile_set_bwd_trace(None, 1)
