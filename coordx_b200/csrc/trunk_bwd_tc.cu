@@ -83,6 +83,25 @@ prep_rows16_kernel(const float* __restrict__ feat, int64_t n, uint8_t* __restric
   if (idx < n * HD) reinterpret_cast<T*>(img)[idx] = to_T<T>(feat[idx]);
 }
 
+// rowvec(o) for the outer indices o of a slab, 16-bit rows: t0[r0 + o / n1] (op) t1[o % n1]   (t1 == nullptr: t0[r0 + o])
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_rowvec16_kernel(const float* __restrict__ t0, const float* __restrict__ t1, int64_t r0, int64_t n1, int64_t n_rows, int op,
+                     uint8_t* __restrict__ img) {
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n_rows * HD) return;
+  const int64_t o = idx >> 8;
+  const int k = (int)(idx & 255);
+  float v;
+  if (t1) {
+    const float a = t0[(r0 + o / n1) * HD + k], b = t1[(o % n1) * HD + k];
+    v = op == COORDX_FUSE_PROD ? a * b : a + b;
+  } else {
+    v = t0[(r0 + o) * HD + k];
+  }
+  reinterpret_cast<T*>(img)[idx] = to_T<T>(v);
+}
+
 constexpr uint32_t CH = 16384;                    // one [128 rows x 128 B] SWIZZLE_128B chunk
 constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB): this CTA's 128 output features of W
 // dH pass:  H 4 chunks | dZ^T 2 chunks | inner block 4 chunks          dW pass:  H stage 0 | H stage 1 | dZ^T 2 chunks
@@ -105,6 +124,7 @@ struct BwdParams {
   int dbg;
   const uint8_t* outer_img;  // optional: the outer0 table as 16-bit rows [n, 256] (512 B each): dH-pass producers fetch rowvec(o) with
                              // the copy engine two tiles ahead instead of global loads on their critical path (outer1 == nullptr only)
+  float* d_inner;            // [n_inner, 256] +=  gradient w.r.t. the inner axis' features (din pass)
   uint8_t* dz_img;           // optional: dZ^T_h tiles, 32 KB per (tile, h), written by the dW pass and read by the drv pass
   const float* consts;       // [256] bias' then [MAX_O][256] wfs (see prep_bwd_consts_kernel)
   const float* outer0;
@@ -1086,6 +1106,219 @@ trunk_bwd_drv_kernel(const BwdParams p) {
   }
 }
 
+// =================================================================================
+// inner-axis gradient pass from the STORED dZ^T tiles (tiling of the dW pass):
+//   d inner[j,k] = sum_o rowvec(o)[k] * sum_n dZ[(o,j),n] W[n,k]
+// For a fixed block of 128 inner rows the sum over the outer index o runs over CONSECUTIVE tiles of a CTA, so the
+// tensor core accumulates it in TMEM:  acc[j,k] += dZ_tile[j,n] . (W_h (.) rowvec(o))[n,k]   (M = 128 j, N = 256 k,
+// K = 128 n of this CTA's half), and the accumulator is flushed with atomics only when the inner block changes
+// (once or twice per CTA).  No G1, no E1, no per-tile epilogue: the producers (W_h in registers, 16-bit) write
+// the scaled weight tile, the copy engine streams the dZ^T tiles and rowvec rows.
+// CTA = 10 warps: 0-7 producers (+ accumulator flush) | 8 tile loader | 9 MMA issuer.
+// =================================================================================
+constexpr int DIN_THREADS = 10 * 32, DIN_DZ_STAGES = 3;
+constexpr uint32_t SMI_WS = 0;                          // 2 stages x 4 chunks: (W_h (.) rowvec)[128 n x 256 k]
+constexpr uint32_t SMI_DZ = 8 * CH;                     // DIN_DZ_STAGES x 2 chunks
+constexpr uint32_t SMI_BAR = SMI_DZ + DIN_DZ_STAGES * 2 * CH;
+constexpr uint32_t SMI_RV = SMI_BAR + 256;              // 2 x 512 B rowvec slots
+constexpr uint32_t SMI_TOTAL = SMI_RV + 1024;
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(DIN_THREADS, 1)
+trunk_bwd_din_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_base + SMI_BAR;
+  const uint32_t b_wsfull = bar0, b_wsempty = bar0 + 16, b_dzfull = bar0 + 32, b_dzempty = bar0 + 64, b_accfull = bar0 + 96,
+                 b_accempty = bar0 + 104, b_rv = bar0 + 112, b_slot = bar0 + 128;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SMI_BAR + 128);
+  constexpr int W_LOAD = 8, W_MMA = 9;
+
+  const int h = blockIdx.x & 1;
+  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int64_t t_begin = total * cta / n_cta;
+  const int64_t t_end = total * (cta + 1) / n_cta;
+  const int my_tiles = (int)(t_end - t_begin);
+  const int n_o32 = (int)n_o;
+  const int64_t jb0 = my_tiles > 0 ? t_begin / n_o : 0;
+  const int o0 = my_tiles > 0 ? (int)(t_begin - jb0 * n_o) : 0;
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(b_wsfull + 8 * c, 8);
+        ptx::mbar_init(b_wsempty + 8 * c, 1);
+        ptx::mbar_init(b_rv + 8 * c, 1);
+      }
+      for (int c = 0; c < DIN_DZ_STAGES; ++c) {
+        ptx::mbar_init(b_dzfull + 8 * c, 1);
+        ptx::mbar_init(b_dzempty + 8 * c, 1);
+      }
+      ptx::mbar_init(b_accfull, 1);
+      ptx::mbar_init(b_accempty, 256);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(b_slot, 256);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tacc = *tmem_slot_gen;
+
+  if (warp == W_LOAD) {
+    // ============================ loader: dZ^T tiles ============================
+    if (my_tiles > 0 && ptx::elect_one()) {
+      for (int t = 0; t < my_tiles; ++t) {
+        const int s = t % DIN_DZ_STAGES;
+        ptx::mbar_wait(b_dzempty + 8 * s, ((t / DIN_DZ_STAGES) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(b_dzfull + 8 * s, 2 * CH);
+        ptx::bulk_g2s(smem_base + SMI_DZ + s * 2 * CH, p.dz_img + ((size_t)(t_begin + t) * 2 + h) * (2 * CH), 2 * CH, b_dzfull + 8 * s);
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_MMA) {
+    // ============================ MMA issuer ============================
+    if (my_tiles > 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 1, 1);   // A = dZ (M = j) MN-major, B = W_h(.)rv (N = k) MN-major
+      int o_local = o0;
+      bool fresh = true;
+      uint32_t flushes = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        if (t > 0 && ++o_local == n_o32) {           // next block of inner rows: hand the accumulator to the flush
+          o_local = 0;
+          ptx::mma_commit(b_accfull);
+          ptx::mbar_wait(b_accempty, flushes & 1);
+          ++flushes;
+          ptx::tc_fence_after();
+          fresh = true;
+        }
+        const int s = t % DIN_DZ_STAGES, st = t & 1;
+        ptx::mbar_wait(b_dzfull + 8 * s, (t / DIN_DZ_STAGES) & 1);
+        ptx::mbar_wait(b_wsfull + 8 * st, (t >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t dz = smem_base + SMI_DZ + s * 2 * CH, ws = smem_base + SMI_WS + st * 4 * CH;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          ptx::mma_f16_ss(tacc, ptx::umma_desc_mn_sw128(dz + ks * 2048, CH), ptx::umma_desc_mn_sw128(ws + ks * 2048, CH), idesc,
+                          !(fresh && ks == 0));
+        fresh = false;
+        ptx::mma_commit(b_wsempty + 8 * st);
+        ptx::mma_commit(b_dzempty + 8 * s);
+      }
+      ptx::mma_commit(b_accfull);
+    }
+    __syncwarp();
+  } else {
+    // ============================ producers: (W_h (.) rowvec(o)) tile; flush of the accumulator ============================
+    // thread (g = lane, rg = warp) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows n = 16 rg .. 16 rg + 15 of W_h
+    const int g = lane, rg = warp;
+    uint32_t win[16][4];
+    {
+      uint32_t chain = 0;
+#pragma unroll
+      for (int r4 = 0; r4 < 16; r4 += 4) {
+        float4 v0[4], v1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* src = p.w_f32 + (size_t)(h * 128 + rg * 16 + r4 + u) * HD + 8 * g + chain;
+          v0[u] = __ldg(reinterpret_cast<const float4*>(src));
+          v1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          win[r4 + u][0] = Pack<T>::pack(v0[u].x, v0[u].y);
+          win[r4 + u][1] = Pack<T>::pack(v0[u].z, v0[u].w);
+          win[r4 + u][2] = Pack<T>::pack(v1[u].x, v1[u].y);
+          win[r4 + u][3] = Pack<T>::pack(v1[u].z, v1[u].w);
+        }
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(win[r4 + 3][3]));
+      }
+    }
+    auto flush = [&](int64_t jb, uint32_t nflush) {
+      ptx::mbar_wait(b_accfull, nflush & 1);
+      ptx::tc_fence_after();
+      const int q = warp & 3, ch = warp >> 2;
+      const int64_t j = jb * TILE_M + q * 32 + lane;
+      float* drow = p.d_inner + j * HD + ch * 128;
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + ch * 128 + b * 32, r);
+        ptx::tmem_ld_wait();
+        if (j < p.n_inner) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(b_accempty);
+    };
+    int64_t jb = jb0;
+    int o_local = o0;
+    uint32_t nflush = 0;
+    const uint32_t one2 = Pack<T>::pack(1.f, 1.f);
+    if (OP == COORDX_FUSE_PROD && threadIdx.x == 0) {          // rowvec ring prologue
+      int on = o0;
+      for (int u = 0; u < 2 && u < my_tiles; ++u) {
+        ptx::mbar_arrive_expect_tx(b_rv + 8 * u, 512);
+        ptx::bulk_g2s(smem_base + SMI_RV + u * 512, p.outer_img + (size_t)on * 512, 512, b_rv + 8 * u);
+        if (++on == n_o32) on = 0;
+      }
+    }
+    for (int t = 0; t < my_tiles; ++t) {
+      if (t > 0 && ++o_local == n_o32) {
+        o_local = 0;
+        flush(jb, nflush++);
+        ++jb;
+      }
+      uint32_t rv[4] = {one2, one2, one2, one2};
+      if (OP == COORDX_FUSE_PROD) {
+        ptx::mbar_wait(b_rv + 8 * (t & 1), (t >> 1) & 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(smem_gen + SMI_RV + (t & 1) * 512 + g * 16);
+        rv[0] = v.x; rv[1] = v.y; rv[2] = v.z; rv[3] = v.w;
+        ptx::named_bar_sync(2, 256);                 // every producer has read the slot
+        if (threadIdx.x == 0 && t + 2 < my_tiles) {
+          int on = o_local + 2;
+          if (on >= n_o32) on -= n_o32;
+          if (on >= n_o32) on -= n_o32;
+          ptx::mbar_arrive_expect_tx(b_rv + 8 * (t & 1), 512);
+          ptx::bulk_g2s(smem_base + SMI_RV + (t & 1) * 512, p.outer_img + (size_t)on * 512, 512, b_rv + 8 * (t & 1));
+        }
+      }
+      const uint32_t st = t & 1;
+      ptx::mbar_wait(b_wsempty + 8 * st, ((t >> 1) & 1) ^ 1);
+      uint8_t* dst = smem_gen + SMI_WS + st * 4 * CH + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        uint4 w;
+        w.x = fuse2<T, COORDX_FUSE_PROD>(win[r][0], rv[0]);
+        w.y = fuse2<T, COORDX_FUSE_PROD>(win[r][1], rv[1]);
+        w.z = fuse2<T, COORDX_FUSE_PROD>(win[r][2], rv[2]);
+        w.w = fuse2<T, COORDX_FUSE_PROD>(win[r][3], rv[3]);
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(b_wsfull + 8 * st);
+    }
+    if (my_tiles > 0) flush(jb, nflush);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tacc, 256);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // small helpers for the 3-axis case
 // ---------------------------------------------------------------------------------
@@ -1195,6 +1428,22 @@ static int launch_drv(const BwdParams& bp, int op, int grid, cudaStream_t st) {
   return 0;
 }
 
+template <typename T>
+static int launch_din(const BwdParams& bp, int op, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_din_kernel<T, COORDX_FUSE_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMI_TOTAL));
+    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_din_kernel<T, COORDX_FUSE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMI_TOTAL));
+    attr_done = true;
+  }
+  if (op == COORDX_FUSE_PROD)
+    trunk_bwd_din_kernel<T, COORDX_FUSE_PROD><<<grid, DIN_THREADS, SMI_TOTAL, st>>>(bp);
+  else
+    trunk_bwd_din_kernel<T, COORDX_FUSE_SUM><<<grid, DIN_THREADS, SMI_TOTAL, st>>>(bp);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
 // dZ^T tiles kept between the dW pass and the d-rowvec pass (64 KB per 128-point tile): on unless
 // COORDX_BWD_DZ_REUSE=0 or the tiles would need more than COORDX_BWD_DZ_MAX_GB (default 24) of workspace
 static bool dz_reuse(int64_t tiles) {
@@ -1230,7 +1479,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   pl.innerA_off = off; off += (size_t)pl.nbA * INNER_BYTES;
   pl.innerB_off = off; off += (size_t)pl.nbB * INNER_BYTES;
   pl.drv_off = off; off += C == 3 ? align_up((size_t)pl.n_oA * HD * 4, 1024) : 0;
-  pl.rows_off = off; off += align_up((size_t)pl.n_innerA * HD * 2, 1024);      // 16-bit rows of the last axis (pass B rowvec)
+  pl.rows_off = off; off += align_up((size_t)max(pl.n_innerA, pl.n_oA) * HD * 2, 1024);   // 16-bit rowvec rows (din pass / pass B)
   pl.reuse = dz_reuse((int64_t)pl.nbA * pl.n_oA);
   pl.dz_off = off; off += pl.reuse ? (size_t)pl.nbA * pl.n_oA * (4 * CH) : 0;
   pl.total = off;
@@ -1294,6 +1543,18 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     CX_LAUNCH_CHECK();
     pair_scatter_kernel<<<(unsigned)cdiv(n1 * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 1, dfeat[1]);
     CX_LAUNCH_CHECK();
+  }
+  if (pl.reuse) {
+    // ---------------- din pass: gradient of the last axis' features from the stored dZ^T tiles (same tiling)
+    prep_rowvec16_kernel<T><<<(unsigned)cdiv(pl.n_oA * HD, 256), 256, 0, st>>>(feats[0], C == 3 ? feats[1] : nullptr, r0, n1, pl.n_oA,
+                                                                              net->fusion_op, base + pl.rows_off);
+    CX_LAUNCH_CHECK();
+    a.outer_img = base + pl.rows_off;
+    a.d_inner = dfeat[C - 1];
+    a.trace = nullptr;
+    const int64_t total = (int64_t)pl.nbA * pl.n_oA;
+    const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
+    return launch_din<T>(a, net->fusion_op, grid, st);
   }
   // ---------------- pass B: roles swapped: tiles = (index on the last axis, 128 outer rows): d(last-axis features)
   if (C == 3)
