@@ -304,7 +304,7 @@ def main():
     if not args.no_train:
         gt = (torch.rand(1, P, 1, device=dev) * 2 - 1)
         gt_host = gt.cpu().pin_memory()
-        opt = torch.optim.Adam(lr=1e-4, params=model.parameters())
+        opt = torch.optim.Adam(lr=1e-4, params=model.parameters(), fused=True)     # training.py:17 (fused = implementation detail)
         xs, ys = x.reshape(1, H, 1, 1), y.reshape(1, 1, W, 1)
 
         def train_step(gtd=gt):

@@ -138,9 +138,21 @@ class _NetDesc:
         return t.data_ptr()
 
 
+def _zeros_like_flat(tensors):
+    """fp32 zero tensors shaped like `tensors`, carved out of ONE zero-filled allocation (a single fill kernel;
+    every piece starts 16-byte aligned)."""
+    sizes = [(int(t.numel()) + 3) // 4 * 4 for t in tensors]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=tensors[0].device)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
+
+
 def _grads_for(block, params):
     g = _lib.Grads()
-    bufs = [torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format) for p in params]
+    bufs = _zeros_like_flat(params)            # one fill for all of them, not one per parameter
     it = iter(bufs)
     for c in range(block.split_channels):
         g.first_w[c] = next(it).data_ptr()
@@ -280,7 +292,7 @@ class _FusionFn(torch.autograd.Function):
         desc = _NetDesc(block, params, n_tables=nfeat)
         grads, bufs = _grads_for(block, params)
         d = _as_f32c(dout)
-        dfeats = [torch.zeros_like(f) for f in feats]
+        dfeats = _zeros_like_flat(feats)
         n_arr = _lib.i64_array(ns)
         f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
         df_arr = _lib.ptr_array([f.data_ptr() for f in dfeats])
@@ -344,6 +356,8 @@ class SplitFCBlock(nn.Module):
         if use_atten:
             raise NotImplementedError('use_atten is ignored by the reference grid path and is out of scope here')
         self.first_layer_init = None
+        self.fork_branches = os.environ.get('COORDX_FORK_BRANCHES', '1') != '0'
+        self._branch_streams = []
         self.coord_dim = coord_dim
         per = in_features // coord_dim
         self.feat_per_channel = [per] * coord_dim if split_rule is None else [per * k for k in split_rule]
@@ -497,7 +511,30 @@ class SplitFCBlock(nn.Module):
 
     def forward(self, coords, params=None, pos_codes=None, split_coord=False, ret_feat=False, **kwargs):
         if split_coord:                                        # modules.py:248-255
-            hs = [self.forward_channel(coord, i, pos_codes) for i, coord in enumerate(coords)]
+            if self.fork_branches and len(coords) > 1 and coords[0].is_cuda:
+                # the per-axis branch MLPs are independent: one stream per branch, joined before the fusion.  Autograd
+                # runs each backward on its forward's stream, so the branch backwards overlap too (and a captured
+                # training step gets parallel graph branches)
+                main = torch.cuda.current_stream(coords[0].device)
+                if len(self._branch_streams) < len(coords):
+                    self._branch_streams = [torch.cuda.Stream(coords[0].device) for _ in coords]
+                    # parameter gradients produced on a branch stream are accumulated on the main stream: intended
+                    # (autograd inserts the synchronisation), not worth a warning per backward
+                    warn_off = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+                    if warn_off is not None:
+                        warn_off(False)
+                hs = []
+                for i, coord in enumerate(coords):
+                    st = self._branch_streams[i]
+                    st.wait_stream(main)
+                    with torch.cuda.stream(st):
+                        h_i = self.forward_channel(coord, i, pos_codes)
+                    h_i.record_stream(main)
+                    hs.append(h_i)
+                for st in self._branch_streams[:len(coords)]:
+                    main.wait_stream(st)
+            else:
+                hs = [self.forward_channel(coord, i, pos_codes) for i, coord in enumerate(coords)]
             h = self.forward_fusion(hs)
             out = h.reshape(h.shape[0], -1, h.shape[-1])
             return (out, hs) if ret_feat else out

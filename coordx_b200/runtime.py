@@ -114,7 +114,7 @@ class CapturedTrainStep:
         self.static_gt = gt.detach().clone()
         self.clip_grad = clip_grad
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = optimizer or torch.optim.Adam(self.params, lr=lr, capturable=True)
+        self.opt = optimizer or torch.optim.Adam(self.params, lr=lr, capturable=True, fused=True)   # one multi-tensor kernel
         if not all(g.get('capturable', False) for g in self.opt.param_groups):
             raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
         if callable(loss):
