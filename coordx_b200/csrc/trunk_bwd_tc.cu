@@ -121,7 +121,6 @@ struct BwdParams {
   const float* inner_f32;    // the same table as fp32 [n_inner, 256]                           (dW pass)
   const float* w_f32;        // trunk weight [256 n_out, 256 k_in] fp32                          (dH pass, E2)
   long long* trace;          // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
-  int dbg;
   const uint8_t* outer_img;  // optional: the outer0 table as 16-bit rows [n, 256] (512 B each): dH-pass producers fetch rowvec(o) with
                              // the copy engine two tiles ahead instead of global loads on their critical path (outer1 == nullptr only)
   float* d_inner;            // [n_inner, 256] +=  gradient w.r.t. the inner axis' features (din pass)
@@ -216,9 +215,9 @@ struct Bars {
 // bias'[n], wfs[o][n] are registers; db[n] and dWf[o][n] are per-thread running sums (no cross-lane reduction).
 // Only the dW pass needs sin (for dWf); the dH passes evaluate cos alone: half the MUFU work.
 // ---------------------------------------------------------------------------------
-template <typename T, int ACT, int O, bool DO_DW>
+template <typename T, int ACT, int O, bool DO_DW, bool DZ_TMEM = false>
 __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint8_t* smem_gen, uint32_t tmem_z0, uint32_t sm_dz,
-                                         int h, int warp, int lane, int my_tiles) {
+                                         int h, int warp, int lane, int my_tiles, int64_t tile0 = 0) {
   const int q = warp & 3, hh = warp >> 2;
   const int row = q * 32 + lane;
   const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
@@ -248,7 +247,7 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
       uint32_t r[16];
       ptx::tmem_ld_32x32b_x16(tmem_z0 + zb * 128 + ((uint32_t)(q * 32) << 16) + hh * 64 + b * 16, r);
       ptx::tmem_ld_wait();
-      if (b == 3) {                                // every Z^T column of this warp is in registers
+      if (b == 3 && !DZ_TMEM) {                    // every Z^T column of this warp is in registers
         ptx::tc_fence_before();
         ptx::mbar_arrive(B.zempty + 8 * zb);
       }
@@ -299,6 +298,25 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
       }
     }
     ptx::mbar_arrive(B.dsempty);                   // last read of the staged dout
+    if (DZ_TMEM) {
+      // dW pass: dZ^T goes back into TENSOR MEMORY, over the first 32 of this warp's own 64 Z^T columns (all of them
+      // are in registers by now), as the A operand of G3: no shared-memory tile, no proxy fence, and G3 reads only
+      // its B operand from shared memory (8 KB per K-step: full rate instead of 68 %).  Safe without extra barriers:
+      // the tensor pipe is in order, G1(t+2) - the next writer of this buffer - is issued after G3(t).
+      if (p.dz_img) {                              // the tile image for the drv / din passes: shared memory, then one bulk store
+        ptx::mbar_wait(B.dzempty, (t & 1) ^ 1);    // the copy engine has read the previous image
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc)
+          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, pc * 8)) = make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+        ptx::fence_proxy_async();
+      }
+      ptx::tmem_st_32x32b_x32(tmem_z0 + zb * 128 + ((uint32_t)(q * 32) << 16) + hh * 64, pk);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(B.dzfull + 8 * hh);
+      if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 3);
+      continue;
+    }
     ptx::mbar_wait(B.dzempty, (t & 1) ^ 1);        // the tensor core is done with dZ(t-1)
     if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 2);
 #pragma unroll
@@ -379,7 +397,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         ptx::mbar_init(B.zempty + 8 * c, 256);
         ptx::mbar_init(B.dzfull + 8 * c, 128);
       }
-      ptx::mbar_init(B.dzempty, p.dz_img ? 2 : 1);  // tensor-core commit (+ the bulk store has read the tile)
+      ptx::mbar_init(B.dzempty, 1);                // the bulk store has read the dZ^T image
       ptx::mbar_init(B.dsfull, 128);
       ptx::mbar_init(B.dsempty, 256);
       ptx::mbar_init(B.w, 1);
@@ -407,7 +425,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
       constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (M = n_out) K-major, B = H (N = k_in) MN-major
       auto issue_g1 = [&](int t) {
         const uint32_t zb = t & 1, use = t >> 1;
-        ptx::mbar_wait(B.zempty + 8 * zb, (use & 1) ^ 1);
+        // (no wait for the Z^T buffer: its last reader is G3(t-2), earlier in this thread's in-order tensor pipe)
         ptx::mbar_wait(B.full + 8 * zb, use & 1);
         ptx::tc_fence_after();
         const uint32_t hs = smem_base + (zb ? SM_H1 : SM_H);
@@ -424,20 +442,17 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         for (int c = 0; c < 2; ++c) {              // K = 128 points, 16 per step; starts on the first 64-point chunk of dZ^T
           ptx::mbar_wait(B.dzfull + 8 * c, t & 1);
           ptx::tc_fence_after();
-          // keep the dZ^T tile for the d-rowvec pass: it then needs neither G1 nor E1 nor an H tile
           if (p.dz_img) ptx::bulk_s2g(p.dz_img + ((size_t)(t_begin + t) * 2 + h) * (2 * CH) + c * CH, smem_base + SM_DZ_DW + c * CH, CH);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int ks = c * 4 + k;
-            ptx::mma_f16_ss(tDW, ptx::umma_desc_k_sw128(smem_base + SM_DZ_DW + c * CH + k * 32),
-                            ptx::umma_desc_mn_sw128(hs + ks * 2048, CH), id_g3, (t | ks) != 0);
+            const int ks = c * 4 + k;              // A = dZ^T in tensor memory: 8 columns (16 points) per K-step
+            ptx::mma_f16_ts(tDW, tZ + (t & 1) * 128 + c * 64 + k * 8, ptx::umma_desc_mn_sw128(hs + ks * 2048, CH), id_g3, (t | ks) != 0);
           }
         }
         ptx::mma_commit(B.empty + 8 * (t & 1));    // H stage free for the producers
-        ptx::mma_commit(B.dzempty);                // dZ^T tile free for E1
         if (p.dz_img) {
           ptx::bulk_commit_group();
-          ptx::bulk_wait_group_read0();            // (the copy engine reads 32 KB while G3 runs)
+          ptx::bulk_wait_group_read0();
           ptx::mbar_arrive(B.dzempty);
         }
       };
@@ -540,7 +555,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
       }
     }
   } else {
-    e1_stage<T, ACT, O, true>(p, B, smem_gen, tZ, SM_DZ_DW, h, warp, lane, my_tiles);
+    e1_stage<T, ACT, O, true, true>(p, B, smem_gen, tZ, SM_DZ_DW, h, warp, lane, my_tiles, t_begin);
     // ---- flush dW_h (accumulated over every tile of this CTA) with one atomic per element
     if (my_tiles > 0) {
       ptx::mbar_wait(B.dwfull, 0);
@@ -642,7 +657,6 @@ trunk_bwd_dh_kernel(const BwdParams p) {
         for (int kc = 0; kc < 4; ++kc) {
           ptx::mbar_wait(B.full + 8 * kc, t & 1);
           ptx::tc_fence_after();
-          if (!(p.dbg & 16))
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(tZ + zb * 128, ptx::umma_desc_k_sw128(smem_base + SM_W + kc * CH + k * 32),
@@ -665,7 +679,6 @@ trunk_bwd_dh_kernel(const BwdParams p) {
           // features; B = dZ^T tile, K-major; K = 128 points = 16 tile rows per step) and E2 is left with a dot
           // product against W[:,k], which is constant for the whole kernel and lives in its registers
           constexpr uint32_t id_g2p = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 1, 0);
-          if (!(p.dbg & 32))
 #pragma unroll
           for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
@@ -996,7 +1009,6 @@ trunk_bwd_drv_kernel(const BwdParams p) {
         }
         const int s = t % DRV_STAGES;
         ptx::mbar_wait(b_dzempty + 8 * s, ((t / DRV_STAGES) & 1) ^ 1);
-        if ((p.dbg & 1) && t >= DRV_STAGES) { ptx::mbar_arrive(b_dzfull + 8 * s); continue; }
         ptx::mbar_arrive_expect_tx(b_dzfull + 8 * s, 2 * CH);
         ptx::bulk_g2s(smem_base + SMR_DZ + s * 2 * CH, p.dz_img + ((size_t)tt * 2 + h) * (2 * CH), 2 * CH, b_dzfull + 8 * s);
       }
@@ -1023,16 +1035,12 @@ trunk_bwd_drv_kernel(const BwdParams p) {
         ptx::tc_fence_after();
         const uint32_t dz = smem_base + SMR_DZ + s * 2 * CH;
         const uint32_t acc = tmem_base + ab * 256;
-        if (!(p.dbg & 2))
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t a = ptx::umma_desc_mn_sw128(smem_base + SMR_OPER + blk * 2 * CH + ks * 2048, CH);
-            if (p.dbg & 4)     // TIMING EXPERIMENT ONLY: K-major A over the same bytes
-              ptx::mma_f16_ss(acc + blk * 128, ptx::umma_desc_k_sw128(smem_base + SMR_OPER + blk * 2 * CH + (ks >> 2) * CH + (ks & 3) * 32),
-                              ptx::umma_desc_k_sw128(dz + (ks >> 2) * CH + (ks & 3) * 32), ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 0), ks != 0);
-            else if (OP == COORDX_FUSE_PROD)
+            if (OP == COORDX_FUSE_PROD)
               ptx::mma_f16_ss(acc + blk * 128, a, ptx::umma_desc_k_sw128(dz + (ks >> 2) * CH + (ks & 3) * 32), id_g2p, ks != 0);
             else
               ptx::mma_f16_ss(acc + blk * 128, a, ptx::umma_desc_mn_sw128(dz + ks * 2048, CH), id_g2, ks != 0);
@@ -1071,7 +1079,6 @@ trunk_bwd_drv_kernel(const BwdParams p) {
       // (16 serialised TMEM round trips = 2.3 k clk per tile for 1 k clk of tensor work)
       const uint32_t tacc = tmem_base + ab * 256 + blk * 128 + ((uint32_t)(q * 32) << 16);
       uint32_t ra[32], rb[32];
-      if (p.dbg & 8) { ptx::tc_fence_before(); ptx::mbar_arrive(b_dhempty + 8 * ab); continue; }
       ptx::tmem_ld_32x32b_x32(tacc, ra);
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -1530,7 +1537,6 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
     a.trace = g_bwd_trace_pass == 0 ? g_bwd_trace : nullptr;
     a.dz_img = pl.reuse ? base + pl.dz_off : nullptr;
-    a.dbg = getenv("COORDX_DBG") ? atoi(getenv("COORDX_DBG")) : 0;
     CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
     a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
     if (pl.reuse)
@@ -1573,7 +1579,6 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   b.d_rv = dfeat[C - 1];
   b.S = S;
   b.trace = g_bwd_trace_pass == 2 ? g_bwd_trace : nullptr;
-  b.dbg = getenv("COORDX_DBG") ? atoi(getenv("COORDX_DBG")) : 0;
   {
     const int64_t total = (int64_t)pl.nbB * n_last;
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
