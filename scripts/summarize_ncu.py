@@ -47,6 +47,30 @@ def launches(path):
         print(f'{c:6d} {v / 1e3:11.1f} {100 * v / total:6.1f}% {v / c / 1e3:10.1f}  {name[:110]}')
 
 
+def launches_multi(path):
+    """launch list with several metrics per launch: one row per launch"""
+    rows = list(csv.reader(open(path, errors='replace')))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
+    hdr = rows[start]
+    iid, iname, imet, ival, iunit = hdr.index('ID'), hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+    per = OrderedDict()
+    for r in rows[start + 1:]:
+        if len(r) <= ival:
+            continue
+        d = per.setdefault(r[iid], {'kernel': r[iname]})
+        d[r[imet]] = (float(r[ival].replace(',', '')), r[iunit])
+    print(f'# {path}: one row per launch (ncu --clock-control none: cold-cache, serialised)')
+    print(f'{"dur_us":>9} {"tensor%":>8} {"xu%":>6} {"issue%":>7} {"dram_rd_MB":>11} {"dram_wr_MB":>11} {"sm_GHz":>7}  kernel')
+    for d in per.values():
+        g = lambda k: d.get(k, (float('nan'), ''))[0]
+        dur = g('gpu__time_duration.sum')
+        dur_us = dur / 1e3 if d.get('gpu__time_duration.sum', (0, 'ns'))[1] in ('ns', 'nsecond') else dur
+        print(f'{dur_us:9.1f} {g("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"):8.1f} '
+              f'{g("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"):6.1f} '
+              f'{g("smsp__issue_active.avg.pct_of_peak_sustained_active"):7.1f} {g("dram__bytes_read.sum") / 1e6:11.1f} '
+              f'{g("dram__bytes_write.sum") / 1e6:11.1f} {g("gpc__cycles_elapsed.avg.per_second") / 1e9:7.3f}  {d["kernel"][:90]}')
+
+
 def full(path):
     out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -60,4 +84,4 @@ def full(path):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'launches_multi': launches_multi, 'full': full}[sys.argv[1]](sys.argv[2])
