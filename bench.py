@@ -128,6 +128,11 @@ def cpu_reference(steps, warmup, budget_s=20.0, train=False):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): everything else that libraries print there (e.g. NCCL's version
+    # banner at communicator creation) is sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -158,7 +163,7 @@ def main():
                 'dtype': 'f32', 'data': 'synthetic', 'config': config,
                 'cpu_baseline': {'value': r['value'], 'unit': unit, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
                 'e2e': {'value': r['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     import torch
@@ -357,7 +362,7 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': unit, 'h2d_bytes_per_step': (H + W) * 4, 'd2h_bytes_per_step': P * 4},
                 'gpu_launches': int(launches_per_step) * args.steps, 'gpu_launches_per_step': int(launches_per_step),
                 'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks, 'train': train}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
