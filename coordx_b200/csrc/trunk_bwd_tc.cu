@@ -1117,15 +1117,23 @@ trunk_bwd_drv_kernel(const BwdParams p) {
 // inner-axis gradient pass from the STORED dZ^T tiles (tiling of the dW pass):
 //   d inner[j,k] = sum_o rowvec(o)[k] * sum_n dZ[(o,j),n] W[n,k]
 // For a fixed block of 128 inner rows the sum over the outer index o runs over CONSECUTIVE tiles of a CTA, so the
-// tensor core accumulates it in TMEM:  acc[j,k] += dZ_tile[j,n] . (W_h (.) rowvec(o))[n,k]   (M = 128 j, N = 256 k,
-// K = 128 n of this CTA's half), and the accumulator is flushed with atomics only when the inner block changes
-// (once or twice per CTA).  No G1, no E1, no per-tile epilogue: the producers (W_h in registers, 16-bit) write
-// the scaled weight tile, the copy engine streams the dZ^T tiles and rowvec rows.
-// CTA = 10 warps: 0-7 producers (+ accumulator flush) | 8 tile loader | 9 MMA issuer.
+// tensor core accumulates it in TMEM and the accumulator is flushed with atomics only when the inner block changes
+// (once or twice per CTA).  Computed transposed,  acc^T[k,j] += (W_h (.) rowvec(o))^T[k,n] . dZ^T_tile[n,j]
+// (two M-blocks of 128 input features k, N = 128 j, K = 128 n of this CTA's half), because then
+//   * the per-tile operand (W_h scaled by rowvec(o)) has k on the TMEM LANE: thread k keeps its W column in 64
+//     registers (16-bit pairs), scales it by ONE scalar rowvec(o)[k] and writes it straight into tensor memory as the
+//     A operand (tcgen05.st) - no shared-memory tile, no proxy fence;
+//   * the MMA reads only the streamed dZ^T tile from shared memory (4 KB per K-step: the operand-fetch limit of
+//     ~70 B/clk is not hit, unlike the SS form with 12 KB per step which ran at 68 %).
+// No G1, no E1, no per-tile epilogue; the copy engine streams the dZ^T tiles (4-deep ring) and the rowvec rows.
+// CTA = 10 warps: 0-7 scalers (+ accumulator flush; warp = (lane quadrant, M-block)) | 8 tile loader | 9 MMA issuer.
+// TMEM: acc^T 2 x 128 columns | A operand 2 buffers x 2 M-blocks x 64 columns.
 // =================================================================================
-constexpr int DIN_THREADS = 10 * 32, DIN_DZ_STAGES = 3;
-constexpr uint32_t SMI_WS = 0;                          // 2 stages x 4 chunks: (W_h (.) rowvec)[128 n x 256 k]
-constexpr uint32_t SMI_DZ = 8 * CH;                     // DIN_DZ_STAGES x 2 chunks
+#ifndef COORDX_DIN_EXP
+#define COORDX_DIN_EXP 0          // timing experiments only: 1 = no MMAs, 2 = no tile loads
+#endif
+constexpr int DIN_THREADS = 10 * 32, DIN_DZ_STAGES = 4;
+constexpr uint32_t SMI_DZ = 0;                          // DIN_DZ_STAGES x 2 chunks
 constexpr uint32_t SMI_BAR = SMI_DZ + DIN_DZ_STAGES * 2 * CH;
 constexpr uint32_t SMI_RV = SMI_BAR + 256;              // 2 x 512 B rowvec slots
 constexpr uint32_t SMI_TOTAL = SMI_RV + 1024;
@@ -1139,7 +1147,7 @@ trunk_bwd_din_kernel(const BwdParams p) {
   uint8_t* smem_gen = smem_raw;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_base + SMI_BAR;
-  const uint32_t b_wsfull = bar0, b_wsempty = bar0 + 16, b_dzfull = bar0 + 32, b_dzempty = bar0 + 64, b_accfull = bar0 + 96,
+  const uint32_t b_afull = bar0, b_aempty = bar0 + 16, b_dzfull = bar0 + 32, b_dzempty = bar0 + 64, b_accfull = bar0 + 96,
                  b_accempty = bar0 + 104, b_rv = bar0 + 112, b_slot = bar0 + 128;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SMI_BAR + 128);
   constexpr int W_LOAD = 8, W_MMA = 9;
@@ -1158,8 +1166,8 @@ trunk_bwd_din_kernel(const BwdParams p) {
   if (warp == W_MMA) {
     if (lane == 0) {
       for (int c = 0; c < 2; ++c) {
-        ptx::mbar_init(b_wsfull + 8 * c, 8);
-        ptx::mbar_init(b_wsempty + 8 * c, 1);
+        ptx::mbar_init(b_afull + 8 * c, 256);
+        ptx::mbar_init(b_aempty + 8 * c, 1);
         ptx::mbar_init(b_rv + 8 * c, 1);
       }
       for (int c = 0; c < DIN_DZ_STAGES; ++c) {
@@ -1171,13 +1179,13 @@ trunk_bwd_din_kernel(const BwdParams p) {
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(b_slot, 256);
+    ptx::tmem_alloc(b_slot, 512);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tacc = *tmem_slot_gen;
+  const uint32_t tacc = *tmem_slot_gen, tA = tacc + 256;
 
   if (warp == W_LOAD) {
     // ============================ loader: dZ^T tiles ============================
@@ -1185,6 +1193,9 @@ trunk_bwd_din_kernel(const BwdParams p) {
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t % DIN_DZ_STAGES;
         ptx::mbar_wait(b_dzempty + 8 * s, ((t / DIN_DZ_STAGES) & 1) ^ 1);
+#if COORDX_DIN_EXP & 2
+        if (t >= DIN_DZ_STAGES) { ptx::mbar_arrive(b_dzfull + 8 * s); continue; }
+#endif
         ptx::mbar_arrive_expect_tx(b_dzfull + 8 * s, 2 * CH);
         ptx::bulk_g2s(smem_base + SMI_DZ + s * 2 * CH, p.dz_img + ((size_t)(t_begin + t) * 2 + h) * (2 * CH), 2 * CH, b_dzfull + 8 * s);
       }
@@ -1193,7 +1204,7 @@ trunk_bwd_din_kernel(const BwdParams p) {
   } else if (warp == W_MMA) {
     // ============================ MMA issuer ============================
     if (my_tiles > 0 && ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 1, 1);   // A = dZ (M = j) MN-major, B = W_h(.)rv (N = k) MN-major
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 128, 0, 1);   // A in tensor memory, B = dZ^T (N = j) MN-major
       int o_local = o0;
       bool fresh = true;
       uint32_t flushes = 0;
@@ -1206,63 +1217,57 @@ trunk_bwd_din_kernel(const BwdParams p) {
           ptx::tc_fence_after();
           fresh = true;
         }
-        const int s = t % DIN_DZ_STAGES, st = t & 1;
+        const int s = t % DIN_DZ_STAGES, ab = t & 1;
         ptx::mbar_wait(b_dzfull + 8 * s, (t / DIN_DZ_STAGES) & 1);
-        ptx::mbar_wait(b_wsfull + 8 * st, (t >> 1) & 1);
+        ptx::mbar_wait(b_afull + 8 * ab, (t >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t dz = smem_base + SMI_DZ + s * 2 * CH, ws = smem_base + SMI_WS + st * 4 * CH;
+        const uint32_t dz = smem_base + SMI_DZ + s * 2 * CH;
+#if !(COORDX_DIN_EXP & 1)
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          ptx::mma_f16_ss(tacc, ptx::umma_desc_mn_sw128(dz + ks * 2048, CH), ptx::umma_desc_mn_sw128(ws + ks * 2048, CH), idesc,
-                          !(fresh && ks == 0));
+#endif
+        for (int blk = 0; blk < ((COORDX_DIN_EXP & 1) ? 0 : 2); ++blk) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            ptx::mma_f16_ts(tacc + blk * 128, tA + ab * 128 + blk * 64 + ks * 8, ptx::umma_desc_mn_sw128(dz + ks * 2048, CH), idesc,
+                            !(fresh && ks == 0));
+        }
         fresh = false;
-        ptx::mma_commit(b_wsempty + 8 * st);
+        ptx::mma_commit(b_aempty + 8 * ab);
         ptx::mma_commit(b_dzempty + 8 * s);
       }
       ptx::mma_commit(b_accfull);
     }
     __syncwarp();
   } else {
-    // ============================ producers: (W_h (.) rowvec(o)) tile; flush of the accumulator ============================
-    // thread (g = lane, rg = warp) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows n = 16 rg .. 16 rg + 15 of W_h
-    const int g = lane, rg = warp;
-    uint32_t win[16][4];
+    // ============================ scalers: A operand = (W_h (.) rowvec(o))^T in tensor memory; accumulator flush ============================
+    const int q = warp & 3, blk = warp >> 2;
+    const int k = blk * 128 + q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t wreg[64];                               // W[128 h + n][k], 16-bit pairs (n = 2i, 2i+1)
     {
       uint32_t chain = 0;
 #pragma unroll
-      for (int r4 = 0; r4 < 16; r4 += 4) {
-        float4 v0[4], v1[4];
+      for (int i4 = 0; i4 < 64; i4 += 4) {
+        float v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float* src = p.w_f32 + (size_t)(h * 128 + rg * 16 + r4 + u) * HD + 8 * g + chain;
-          v0[u] = __ldg(reinterpret_cast<const float4*>(src));
-          v1[u] = __ldg(reinterpret_cast<const float4*>(src + 4));
-        }
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(p.w_f32 + (size_t)(h * 128 + 2 * i4 + u) * HD + k + chain);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          win[r4 + u][0] = Pack<T>::pack(v0[u].x, v0[u].y);
-          win[r4 + u][1] = Pack<T>::pack(v0[u].z, v0[u].w);
-          win[r4 + u][2] = Pack<T>::pack(v1[u].x, v1[u].y);
-          win[r4 + u][3] = Pack<T>::pack(v1[u].z, v1[u].w);
-        }
-        asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(win[r4 + 3][3]));
+        for (int u = 0; u < 4; ++u) wreg[i4 + u] = Pack<T>::pack(v[2 * u], v[2 * u + 1]);
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(wreg[i4 + 3]));
       }
     }
     auto flush = [&](int64_t jb, uint32_t nflush) {
       ptx::mbar_wait(b_accfull, nflush & 1);
       ptx::tc_fence_after();
-      const int q = warp & 3, ch = warp >> 2;
-      const int64_t j = jb * TILE_M + q * 32 + lane;
-      float* drow = p.d_inner + j * HD + ch * 128;
+      float* dcol = p.d_inner + jb * TILE_M * HD + k;            // acc^T[k, j]: lanes = consecutive k (coalesced atomics)
 #pragma unroll 1
       for (int b = 0; b < 4; ++b) {
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + ch * 128 + b * 32, r);
+        ptx::tmem_ld_32x32b_x32(tacc + blk * 128 + lane_base + b * 32, r);
         ptx::tmem_ld_wait();
-        if (j < p.n_inner) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]));
-        }
+        for (int i = 0; i < 32; ++i)
+          if (jb * TILE_M + b * 32 + i < p.n_inner) atomicAdd(dcol + (size_t)(b * 32 + i) * HD, __uint_as_float(r[i]));
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(b_accempty);
@@ -1270,7 +1275,6 @@ trunk_bwd_din_kernel(const BwdParams p) {
     int64_t jb = jb0;
     int o_local = o0;
     uint32_t nflush = 0;
-    const uint32_t one2 = Pack<T>::pack(1.f, 1.f);
     if (OP == COORDX_FUSE_PROD && threadIdx.x == 0) {          // rowvec ring prologue
       int on = o0;
       for (int u = 0; u < 2 && u < my_tiles; ++u) {
@@ -1285,12 +1289,12 @@ trunk_bwd_din_kernel(const BwdParams p) {
         flush(jb, nflush++);
         ++jb;
       }
-      uint32_t rv[4] = {one2, one2, one2, one2};
+      uint32_t rv2 = Pack<T>::pack(1.f, 1.f);        // sum fusion: dH is not scaled
       if (OP == COORDX_FUSE_PROD) {
         ptx::mbar_wait(b_rv + 8 * (t & 1), (t >> 1) & 1);
-        const uint4 v = *reinterpret_cast<const uint4*>(smem_gen + SMI_RV + (t & 1) * 512 + g * 16);
-        rv[0] = v.x; rv[1] = v.y; rv[2] = v.z; rv[3] = v.w;
-        ptx::named_bar_sync(2, 256);                 // every producer has read the slot
+        const uint32_t e = *reinterpret_cast<const uint16_t*>(smem_gen + SMI_RV + (t & 1) * 512 + k * 2);
+        rv2 = e | (e << 16);
+        ptx::named_bar_sync(2, 256);                 // every scaler has read the slot
         if (threadIdx.x == 0 && t + 2 < my_tiles) {
           int on = o_local + 2;
           if (on >= n_o32) on -= n_o32;
@@ -1299,21 +1303,19 @@ trunk_bwd_din_kernel(const BwdParams p) {
           ptx::bulk_g2s(smem_base + SMI_RV + (t & 1) * 512, p.outer_img + (size_t)on * 512, 512, b_rv + 8 * (t & 1));
         }
       }
-      const uint32_t st = t & 1;
-      ptx::mbar_wait(b_wsempty + 8 * st, ((t >> 1) & 1) ^ 1);
-      uint8_t* dst = smem_gen + SMI_WS + st * 4 * CH + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
+      const uint32_t ab = t & 1;
+      uint32_t sc[32];
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        uint4 w;
-        w.x = fuse2<T, COORDX_FUSE_PROD>(win[r][0], rv[0]);
-        w.y = fuse2<T, COORDX_FUSE_PROD>(win[r][1], rv[1]);
-        w.z = fuse2<T, COORDX_FUSE_PROD>(win[r][2], rv[2]);
-        w.w = fuse2<T, COORDX_FUSE_PROD>(win[r][3], rv[3]);
-        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
-      }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(b_wsfull + 8 * st);
+      for (int i = 0; i < 32; ++i) sc[i] = fuse2<T, COORDX_FUSE_PROD>(wreg[i], rv2);
+      ptx::mbar_wait(b_aempty + 8 * ab, ((t >> 1) & 1) ^ 1);     // the tensor core is done with this A buffer (tile t-2)
+      ptx::tc_fence_after();
+      ptx::tmem_st_32x32b_x32(tA + ab * 128 + blk * 64 + lane_base, sc);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sc[i] = fuse2<T, COORDX_FUSE_PROD>(wreg[32 + i], rv2);
+      ptx::tmem_st_32x32b_x32(tA + ab * 128 + blk * 64 + 32 + lane_base, sc);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(b_afull + 8 * ab);
     }
     if (my_tiles > 0) flush(jb, nflush);
   }
@@ -1322,7 +1324,7 @@ trunk_bwd_din_kernel(const BwdParams p) {
   __syncthreads();
   if (warp == W_MMA) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tacc, 256);
+    ptx::tmem_dealloc(tacc, 512);
   }
 }
 
