@@ -6,6 +6,7 @@
 //   TN  dW[N,K]+= dZ[M,N]^T . X[M,K]  (split over M, atomics)
 #pragma once
 #include "common.cuh"
+#include "gemm_tf32x3.cuh"
 
 namespace coordx {
 
@@ -223,6 +224,12 @@ static int linear_forward(const float* X, int64_t ldx, const float* W, const flo
     linear_narrow_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, W, bias, bscale, M, N, K, Y, Z, ldc, act, S);
     CX_LAUNCH_CHECK();
     return 0;
+  }
+  {                                                   // large layers: fp32-accurate 3xTF32 on the tensor cores
+    g3::Args t{};
+    t.A = X; t.lda = ldx; t.B = W; t.ldb = K; t.M = M; t.N = N; t.K = K;
+    t.Y = Y; t.Z = Z; t.ldc = ldc; t.cs = 1; t.bias = bias; t.bscale = bscale; t.act = act; t.S = S;
+    if (g3::usable(t)) return g3::launch(t, st);
   }
   GemmArgs g{};
   g.A = X; g.lda = ldx; g.B = W; g.ldb = K; g.M = M; g.N = N; g.K = K;

@@ -53,7 +53,7 @@ static Plan make_plan(const coordx_net* net, const int64_t* n, int64_t r0, int64
   p.Kin = net->hidden;
   p.Nh = net->layer_out[net->n_pre];
   p.O = net->layer_out[net->n_layers - 1];
-  p.K1 = 2 * p.Nh + 1;
+  p.K1 = 2 * p.Nh + 4;              // table row stride: [2Nh values | bias or 1 | 3 unused], 16-byte aligned rows
   p.R = r1 - r0;
   p.inner = 1;
   p.inner2 = 1;
@@ -90,7 +90,7 @@ table_outer_kernel(const float* __restrict__ U, const float* __restrict__ Wf, co
   if (idx >= rows * Nh) return;
   const int64_t i = idx / Nh;
   const int n = (int)(idx % Nh);
-  const int K1 = 2 * Nh + 1;
+  const int K1 = 2 * Nh + 4;
   float s, c;
   sincos_accurate(S * U[idx], &s, &c);
   for (int o = 0; o < O; ++o) {
@@ -203,10 +203,19 @@ static int forward(const coordx_net* net, const float* const* feats, const int64
       table_cs_kernel<<<(unsigned)cdiv(cnt * p.Nh, 256), 256, 0, st>>>(b.V, S, cnt, p.Nh, p.K1, b.TV);
       CX_LAUNCH_CHECK();
       for (int o = 0; o < p.O; ++o) {      // out[(i, j), o] = TU[(i,o), :] . TV[j, :]
+        {                                    // large grids: 3xTF32 on the tensor cores, K = 2Nh, bf[o] added in the epilogue
+          g3::Args t{};
+          t.A = b.TU + (int64_t)o * p.K1; t.lda = (int64_t)p.O * p.K1;
+          t.B = b.TV; t.ldb = p.K1;
+          t.M = (int)rows; t.N = (int)cnt; t.K = 2 * p.Nh;
+          t.Y = out + (ra * p.inner + j0) * p.O + o; t.ldc = p.inner * p.O; t.cs = p.O;
+          t.bias1 = net->layer_b[Lf] ? net->layer_b[Lf] + o : nullptr; t.act = -1;
+          if (g3::usable(t)) { CX_TRY(g3::launch(t, st)); continue; }
+        }
         GemmArgs g{};
         g.A = b.TU + (int64_t)o * p.K1; g.lda = (int64_t)p.O * p.K1;
         g.B = b.TV; g.ldb = p.K1;
-        g.M = (int)rows; g.N = (int)cnt; g.K = p.K1;
+        g.M = (int)rows; g.N = (int)cnt; g.K = 2 * p.Nh + 1;
         g.Y = out + (ra * p.inner + j0) * p.O + o; g.ldc = p.inner * p.O; g.cs = p.O;
         g.act = -1;
         CX_TRY((launch_sgemm<true, true, EPI_LINEAR>(g, st)));
