@@ -108,13 +108,21 @@ class CapturedTrainStep:
     parameters and optimizer state are restored to their values at construction."""
 
     def __init__(self, model: 'M.SingleBVPNet', coords: Sequence[torch.Tensor], gt: torch.Tensor, loss='mse',
-                 lr: float = 1e-4, clip_grad: bool = False, optimizer: torch.optim.Optimizer = None, warmup: int = 3):
+                 lr: float = 1e-4, clip_grad: bool = False, optimizer: torch.optim.Optimizer = None, warmup: int = 3,
+                 lr_gamma: float = None):
         self.model = model
         self.static_coords = [c.detach().clone() for c in coords]
         self.static_gt = gt.detach().clone()
         self.clip_grad = clip_grad
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = optimizer or torch.optim.Adam(self.params, lr=lr, capturable=True, fused=True)   # one multi-tensor kernel
+        # lr_gamma: the reference's ExponentialLR (training.py:25, stepped once per iteration :146) as a device-side
+        # schedule: the learning rate is a device scalar that the captured iteration itself decays
+        self.lr_gamma = lr_gamma
+        self.lr_t = torch.tensor(float(lr), device=self.static_gt.device) if lr_gamma is not None else None
+        if lr_gamma is not None and optimizer is not None:
+            raise ValueError('lr_gamma needs the built-in optimizer (its learning rate is a device tensor)')
+        self.opt = optimizer or torch.optim.Adam(self.params, lr=self.lr_t if lr_gamma is not None else lr,
+                                                 capturable=True, fused=True)   # one multi-tensor kernel
         if not all(g.get('capturable', False) for g in self.opt.param_groups):
             raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
         if callable(loss):
@@ -141,6 +149,8 @@ class CapturedTrainStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._iteration()
         with torch.no_grad():                                    # undo the warm-up updates
+            if self.lr_t is not None:
+                self.lr_t.fill_(float(lr))
             for p, s in zip(self.params, saved_p):
                 p.copy_(s)
             for p in self.params:
@@ -157,6 +167,8 @@ class CapturedTrainStep:
         if self.clip_grad:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=1.)
         self.opt.step()
+        if self.lr_t is not None:
+            self.lr_t.mul_(self.lr_gamma)
         return loss
 
     def set_batch(self, coords: Sequence[torch.Tensor] = None, gt: torch.Tensor = None) -> None:
