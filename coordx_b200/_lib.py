@@ -78,6 +78,10 @@ SIGNATURES = {
                                         C.c_size_t, C.c_void_p]),
     'coordx_branch_backward': (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(Grads),
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'coordx_branch_forward_save': (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p]),
+    'coordx_branch_backward_saved': (C.c_int, [C.POINTER(Net), C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.POINTER(Grads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'coordx_trunk_workspace_bytes': (C.c_size_t, [C.POINTER(Net), _I64P, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     'coordx_trunk_forward': (C.c_int, [C.POINTER(Net), _PP, _I64P, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -117,7 +121,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.coordx_abi_version() != 1:
+        if lib.coordx_abi_version() != 2:
             raise CoordxError('libcoordx_b200.so ABI version mismatch')
         _lib = lib
     return _lib

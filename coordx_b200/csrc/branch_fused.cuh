@@ -30,7 +30,22 @@ struct BranchArgs {
   const float* first_b[COORDX_MAX_BRANCHES];
   const float* w[COORDX_MAX_LAYERS];
   const float* b[COORDX_MAX_LAYERS];
+  // training mode (nullable): pre-activation / activation of every layer, [n_c, 256] each, kept for the backward
+  // pass (layer 0 = coord_linears[c], layer l + 1 = net[l]); the last layer's activation is `feat` itself
+  float* zsave[COORDX_MAX_BRANCHES][COORDX_MAX_LAYERS + 1];
+  float* asave[COORDX_MAX_BRANCHES][COORDX_MAX_LAYERS + 1];
 };
+
+// coalesced copy of the CTA's [16, 256] activation rows to a [n, 256] global array
+// (dst is CTA-uniform; sync_after: the rows are overwritten in place by the activation pass that follows)
+__device__ __forceinline__ void store_rows(float* dst, const float* h, int64_t r0, int64_t n, int tid, bool sync_after) {
+  if (!dst) return;
+  for (int i = tid; i < 16 * 256 / 4; i += 128) {
+    const int r = i / (256 / 4);
+    if (r0 + r < n) reinterpret_cast<float4*>(dst + (r0 + r) * 256)[i % (256 / 4)] = reinterpret_cast<const float4*>(h + r * 256)[i % (256 / 4)];
+  }
+  if (sync_after) __syncthreads();
+}
 
 __device__ __forceinline__ float act_exact(int act, float S, float z) { return act_fwd(act, S, z); }
 
@@ -90,10 +105,12 @@ branch_fused_fwd_kernel(const BranchArgs a) {
       for (int cc = 0; cc < 4; ++cc) hbuf[0][rg * 8 + r][cg + 64 * cc] = acc[r][cc];
   }
   __syncthreads();
+  store_rows(a.zsave[c][0], &hbuf[0][0][0], r0, n, tid, true);
   // the activation runs as a ROLLED pass over shared memory: the accurate sinf is ~60 instructions, and 32 inlined
   // copies per layer made the kernel 160 KB of code - 40 % of its stalls were instruction-cache misses
   apply_act(&hbuf[0][0][0], a.act, a.S, tid);
   __syncthreads();
+  if (a.n_pre > 0) store_rows(a.asave[c][0], &hbuf[0][0][0], r0, n, tid, false);
 
   // ---- net[0 .. n_pre-1]: bias / C (modules.py:224-229); the last one without activation when fusion_before_act
   int cur = 0;
@@ -162,10 +179,12 @@ branch_fused_fwd_kernel(const BranchArgs a) {
     }
     __syncthreads();
     cur ^= 1;
+    store_rows(a.zsave[c][l + 1], &hbuf[cur][0][0], r0, n, tid, true);
     if (!noact) {
       apply_act(&hbuf[cur][0][0], a.act, a.S, tid);
       __syncthreads();
     }
+    if (!last) store_rows(a.asave[c][l + 1], &hbuf[cur][0][0], r0, n, tid, false);
     if (last) {                                   // coalesced write of the [16, 256] feature rows
       for (int i = tid; i < ROWS * WIDTH / 4; i += THREADS) {
         const int r = i / (WIDTH / 4);
@@ -193,7 +212,7 @@ static bool supported(const coordx_net* net) {
 
 // branches [c_begin, c_end) in one launch
 static int launch(const coordx_net* net, int c_begin, int c_end, const float* const* coords, const int64_t* n,
-                  float* const* feat, cudaStream_t st) {
+                  float* const* feat, cudaStream_t st, float* const* zsave = nullptr, float* const* asave = nullptr) {
   BranchArgs a{};
   a.n_branches = c_end - c_begin;
   a.n_pre = net->n_pre;
@@ -212,6 +231,8 @@ static int launch(const coordx_net* net, int c_begin, int c_end, const float* co
     a.first_b[i] = net->first_b[c];
     a.blk0[i] = blocks;
     blocks += (int)cdiv(n[i], ROWS);
+    if (zsave && c_end - c_begin == 1)                 // training mode: one branch per call
+      for (int l = 0; l <= net->n_pre; ++l) { a.zsave[i][l] = zsave[l]; a.asave[i][l] = asave[l]; }
   }
   a.blk0[a.n_branches] = blocks;
   for (int k = 0; k < net->n_pre; ++k) { a.w[k] = net->layer_w[k]; a.b[k] = net->layer_b[k]; }

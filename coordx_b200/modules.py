@@ -195,7 +195,9 @@ def _net_desc(block, params, n_tables=None):
     return d
 
 
-def _branch_forward(block, branch, coords, params):
+def _branch_forward(block, branch, coords, params, save=False):
+    """forward_channel through the C ABI.  save=True (training): the branch activations are kept in a buffer of
+    their own for coordx_branch_backward_saved instead of being recomputed by the backward pass."""
     lib = _lib.load()
     x = _as_f32c(coords)
     if not x.is_cuda:
@@ -203,12 +205,19 @@ def _branch_forward(block, branch, coords, params):
     n = x.shape[0]
     desc = _net_desc(block, params)
     feat = torch.empty(n, block.fuse_width, dtype=torch.float32, device=x.device)
+    saved = None
     with torch.cuda.device(x.device):
-        ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 0)
-        ws = _workspace(ws_bytes, x.device)
-        _lib.check(lib.coordx_branch_forward(desc.net, branch, x.data_ptr(), n, feat.data_ptr(), ws.data_ptr(),
-                                             ws.numel(), _stream_ptr()), 'coordx_branch_forward')
-    return feat, x
+        if save:
+            ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 1)
+            saved = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.coordx_branch_forward_save(desc.net, branch, x.data_ptr(), n, feat.data_ptr(), saved.data_ptr(),
+                                                      saved.numel(), _stream_ptr()), 'coordx_branch_forward_save')
+        else:
+            ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 0)
+            ws = _workspace(ws_bytes, x.device)
+            _lib.check(lib.coordx_branch_forward(desc.net, branch, x.data_ptr(), n, feat.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), _stream_ptr()), 'coordx_branch_forward')
+    return feat, x, saved
 
 
 def _fusion_forward(block, precision, feats, params):
@@ -243,8 +252,8 @@ class _BranchFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, block, branch, coords, *params):
-        feat, x = _branch_forward(block, branch, coords, params)
-        ctx.block, ctx.branch = block, branch
+        feat, x, saved = _branch_forward(block, branch, coords, params, save=True)
+        ctx.block, ctx.branch, ctx.saved_acts = block, branch, saved
         ctx.save_for_backward(x, *params)
         return feat
 
@@ -259,11 +268,11 @@ class _BranchFn(torch.autograd.Function):
         d = _as_f32c(dfeat)
         dcoords = torch.empty_like(x) if ctx.needs_input_grad[2] else None
         with torch.cuda.device(x.device):
-            ws_bytes = lib.coordx_branch_workspace_bytes(desc.net, branch, n, 1)
-            ws = _workspace(ws_bytes, x.device)
-            _lib.check(lib.coordx_branch_backward(desc.net, branch, x.data_ptr(), n, d.data_ptr(), grads,
-                                                  dcoords.data_ptr() if dcoords is not None else None,
-                                                  ws.data_ptr(), ws.numel(), _stream_ptr()), 'coordx_branch_backward')
+            ws = ctx.saved_acts                     # written by coordx_branch_forward_save
+            _lib.check(lib.coordx_branch_backward_saved(desc.net, branch, x.data_ptr(), n, d.data_ptr(), grads,
+                                                        dcoords.data_ptr() if dcoords is not None else None,
+                                                        ws.data_ptr(), ws.numel(), _stream_ptr()),
+                       'coordx_branch_backward_saved')
         used = block.branch_param_mask(branch)
         out = [b if (u and ctx.needs_input_grad[3 + i]) else None for i, (b, u) in enumerate(zip(bufs, used))]
         return (None, None, dcoords, *out)

@@ -127,10 +127,9 @@ class CapturedTrainStep:
             raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
         if callable(loss):
             self.loss_fn = loss
-        elif loss == 'mse':
-            self.loss_fn = lambda out, gt_: ((out - gt_) ** 2).mean()
-        elif loss == 'bce':
-            self.loss_fn = lambda out, gt_: torch.nn.functional.binary_cross_entropy_with_logits(out, gt_)
+        elif loss in ('mse', 'bce'):                 # one kernel: value and d loss / d out (loss_functions.py)
+            from .loss_functions import fused_loss
+            self.loss_fn = lambda out, gt_: fused_loss(loss, out, gt_, unit_grad=True)
         else:
             raise ValueError(f'unknown loss {loss!r}')
         saved_p = [p.detach().clone() for p in self.params]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define COORDX_ABI_VERSION 1
+#define COORDX_ABI_VERSION 2
 #define COORDX_MAX_BRANCHES 4
 #define COORDX_MAX_LAYERS 12
 
@@ -108,6 +108,16 @@ int coordx_branch_forward(const coordx_net* net, int branch, const float* coords
 int coordx_branch_backward(const coordx_net* net, int branch, const float* coords, int64_t n,
                            const float* dfeat, coordx_grads* grads, float* dcoords,
                            void* ws, size_t ws_bytes, void* stream);
+
+/* training-mode pair (what autograd's saved tensors are in the reference, modules.py:26-27,39): the forward also
+ * keeps every layer's pre-activation / activation in `save` (coordx_branch_workspace_bytes(net, branch, n, 1)
+ * bytes, owned by the caller until the matching backward call), the backward starts from them.  The weight- and
+ * bias-gradient kernels run on an internal side stream that is forked from and joined back into `stream`.        */
+int coordx_branch_forward_save(const coordx_net* net, int branch, const float* coords, int64_t n,
+                               float* feat, void* save, size_t save_bytes, void* stream);
+int coordx_branch_backward_saved(const coordx_net* net, int branch, const float* coords, int64_t n,
+                                 const float* dfeat, coordx_grads* grads, float* dcoords,
+                                 void* save, size_t save_bytes, void* stream);
 
 /* ---- fusion + trunk: SplitFCBlock.forward_fusion, modules.py:329-354 -----------------
  * feats[c] [n[c], fuse_width]  ->  out [(row_end-row_begin) * prod_{c>0} n[c], out_width]
