@@ -245,13 +245,19 @@ int coordx_trunk_tc_supported(const coordx_net* net, int precision) {
 }
 
 // -------------------------------------------------------------------------- branch
+// inference over many rows (the scattered-point path: one "axis sample" per query point): rows are pushed through the
+// per-layer GEMM chain in chunks of this many, so the workspace is bounded and the 3xTF32 tensor-core GEMM takes the
+// 256-wide layers (the fused FFMA kernel below is built for a few thousand axis samples)
+constexpr int64_t BRANCH_CHUNK = 65536;
+constexpr int64_t BRANCH_FUSED_MAX = 32768;
+
 size_t coordx_branch_workspace_bytes(const coordx_net* net, int branch, int64_t n, int backward) {
   if (check_net(net) != 0 || branch < 0 || branch >= net->n_branches) return 0;
   Layer L[COORDX_MAX_LAYERS + 1];
   const int nl = branch_layers(net, branch, nullptr, L);
   Arena ar(nullptr, 0);
   ChainWs w{};
-  carve_chain(ar, L, nl, n, backward != 0, w);
+  carve_chain(ar, L, nl, backward ? n : min(n, BRANCH_CHUNK), backward != 0, w);
   return ar.off + 256;
 }
 
@@ -261,15 +267,20 @@ int coordx_branch_forward(const coordx_net* net, int branch, const float* coords
   if (branch < 0 || branch >= net->n_branches) return set_err(COORDX_ERR_ARG, "branch out of range%s (%lld)", "", branch);
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (bf::supported(net)) return bf::launch(net, branch, branch + 1, &coords, &n, &feat, st);
+  if (bf::supported(net) && n <= BRANCH_FUSED_MAX) return bf::launch(net, branch, branch + 1, &coords, &n, &feat, st);
   Layer L[COORDX_MAX_LAYERS + 1];
   const int nl = branch_layers(net, branch, nullptr, L);
   Arena ar(ws, ws_bytes);
   ChainWs w{};
-  carve_chain(ar, L, nl, n, false, w);
+  carve_chain(ar, L, nl, min(n, BRANCH_CHUNK), false, w);
   if (!ar.ok() || (nl > 1 && !w.tmp0)) return set_err(COORDX_ERR_WORKSPACE, "branch forward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
-  return mlp_forward(L, nl, coords, net->branch_in[branch], (int)n, feat, nullptr, nullptr, w.tmp0, w.tmp1,
-                     30.f * net->act_scale, st);
+  const int f = net->branch_in[branch];
+  for (int64_t r0 = 0; r0 < n; r0 += BRANCH_CHUNK) {
+    const int rows = (int)min(BRANCH_CHUNK, n - r0);
+    CX_TRY(mlp_forward(L, nl, coords + r0 * f, f, rows, feat + r0 * L[nl - 1].out, nullptr, nullptr, w.tmp0, w.tmp1,
+                       30.f * net->act_scale, st));
+  }
+  return 0;
 }
 
 int coordx_branch_backward(const coordx_net* net, int branch, const float* coords, int64_t n, const float* dfeat,

@@ -9,9 +9,12 @@ libcoordx_b200.so (hand-written sm_100a CUDA behind the C ABI of
 include/coordx_b200.h).  PyTorch provides parameters, device memory, streams and
 autograd plumbing only.
 
-Not on the hot path and kept as plain torch ops (SURVEY 8f "next"): the
-scattered-point path `{'coords': ...}` (modules.py:257-309, needed by summaries and
-coordinate-gradient losses) and the un-split FCBlock baseline.
+The scattered-point path `{'coords': ...}` (modules.py:257-309; SURVEY 8f "next" rank 1)
+runs through the same kernels whenever no second derivative with respect to the
+coordinates can be asked for (`SplitFCBlock.scattered_impl`); with grad mode on and
+coordinates that require grad (summaries, diff_operators.gradient / laplace, the SDF
+loss) it stays the reference's torch-op sequence.  The un-split FCBlock baseline is
+plain torch ops.
 """
 from __future__ import annotations
 
@@ -23,6 +26,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 from torch import nn
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -258,6 +262,7 @@ class _BranchFn(torch.autograd.Function):
         return feat
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dfeat):
         lib = _lib.load()
         x, *params = ctx.saved_tensors
@@ -291,6 +296,7 @@ class _FusionFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, dout):
         lib = _lib.load()
         block, nfeat = ctx.block, ctx.nfeat
@@ -549,9 +555,42 @@ class SplitFCBlock(nn.Module):
             return (out, hs) if ret_feat else out
         return self._forward_scattered(coords, pos_codes, ret_feat)
 
+    def _forward_scattered_fused(self, coords, ret_feat=False):
+        """modules.py:257-309 through the same kernels as the grid path: every query point is one 'axis sample' of
+        every branch (C branch-MLP calls over P rows: the per-layer 3xTF32 GEMM chain for large P), the per-point
+        fusion is one elementwise pass, and the trunk sees a 1 x P grid whose first axis is the fusion's neutral
+        element - so the tcgen05 trunk (or the separable sum evaluation) serves scattered points unchanged."""
+        lead = coords.shape[:-1]
+        x = coords.reshape(-1, coords.shape[-1])
+        parts = torch.split(x, self.feat_per_channel, dim=-1)
+        feats = [self.forward_channel(p_.contiguous(), c) for c, p_ in enumerate(parts)]       # C x [P, F]
+        h = feats[0]
+        for f_ in feats[1:]:
+            h = h + f_ if self.fusion_operator == 'sum' else h * f_
+        neutral = (torch.zeros if self.fusion_operator == 'sum' else torch.ones)(1, h.shape[-1], dtype=h.dtype, device=h.device)
+        params = self.abi_params()
+        if _needs_grad([h, *params]):
+            out = _FusionFn.apply(self, None, 2, neutral, h, *params)
+        else:
+            out = _fusion_forward(self, None, [neutral, h], params)[0]
+        out = out.reshape(*lead, out.shape[-1])
+        if ret_feat:
+            return out, torch.stack([f_.reshape(*lead, f_.shape[-1]) for f_ in feats], -2)
+        return out
+
     def _forward_scattered(self, coords, pos_codes=None, ret_feat=False):
-        """Arbitrary points [..., sum f_c] (modules.py:257-309) - torch ops, differentiable
-        w.r.t. coords (diff_operators.gradient, utils.write_image_summary)."""
+        """Arbitrary points [..., sum f_c] (modules.py:257-309).  `scattered_impl`: 'auto' (default) takes the CUDA
+        kernels unless gradients with respect to the coordinates may be asked for (grad mode on and
+        coords.requires_grad: diff_operators.gradient / laplace differentiate twice, which only the torch-op
+        formulation supports); 'fused' always takes the kernels (first derivatives only; a second differentiation
+        raises); 'eager' is the reference's op sequence."""
+        impl = getattr(self, 'scattered_impl', 'auto')
+        if impl not in ('auto', 'fused', 'eager'):
+            raise ValueError(f'unknown scattered_impl {impl!r}')
+        wants_coord_grad = torch.is_grad_enabled() and coords.requires_grad
+        if coords.is_cuda and pos_codes is None and coords.numel() > 0 and 2 <= _lib.MAX_BRANCHES and \
+                (impl == 'fused' or (impl == 'auto' and not wants_coord_grad)):
+            return self._forward_scattered_fused(coords, ret_feat)
         al = self.approx_layers
         parts = torch.split(coords, self.feat_per_channel, dim=-1)
         hs = torch.stack([lin(x) for lin, x in zip(self.coord_linears, parts)], -2)
