@@ -40,6 +40,35 @@ static int mlp_forward(const Layer* L, int nl, const float* X, int64_t ldx, int 
   return 0;
 }
 
+// Wt[c, r] = W[r, c]
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wt) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < rows && c0 + tx < cols) t[i][tx] = W[(size_t)(r0 + i) * cols + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) Wt[(size_t)(c0 + i) * rows + r0 + tx] = t[tx][i];
+}
+
+// dX[M,K] = dZ[M,N] W[N,K] (* act'(Zprev)) on the tensor cores (3xTF32) when the shape pays: W is transposed into `wt`
+// first so that both operands are K-major.  Returns 1 when it launched, 0 when the caller should take the FFMA kernel.
+static int dx_tensor(const float* dZ, int64_t lddz, const float* W, int M, int N, int K, float* dX, int64_t lddx,
+                     const float* Zprev, int64_t ldz, int act, float S, float* wt, cudaStream_t st, int* launched) {
+  *launched = 0;
+  if (!wt) return 0;
+  g3::Args t{};
+  t.A = dZ; t.lda = lddz; t.B = wt; t.ldb = N; t.M = M; t.N = K; t.K = N;
+  t.Y = dX; t.ldc = lddx; t.cs = 1; t.act = Zprev ? act : -1; t.S = S; t.zprev = Zprev; t.ldz = ldz;
+  if (!g3::usable(t)) return 0;
+  dim3 grid((unsigned)cdiv(K, 32), (unsigned)cdiv(N, 32));
+  transpose_kernel<<<grid, 256, 0, st>>>(W, N, K, wt);
+  CX_LAUNCH_CHECK();
+  CX_TRY(g3::launch(t, st));
+  *launched = 1;
+  return 0;
+}
+
 // Side stream of a backward chain: the weight- and bias-gradient kernels of a layer only CONSUME dz_l, the chain
 // itself continues with dX.  On one stream a 3-layer branch backward is 3 x (dW, colsum, dX) small launch-latency-bound
 // GEMMs in a row (250 us per 2048-sample axis, measured inside the captured training step); forked, the critical path
@@ -67,7 +96,8 @@ static int get_fork(int slot, Fork** out) {
 // Backward of mlp_forward.  dY = gradient w.r.t. the chain output.  d0/d1: scratch of
 // M * max width floats.  dX (nullable) [M, L[0].in].  fork (nullable): run dW / db on its side stream.
 static int mlp_backward(const Layer* L, int nl, const float* X, int64_t ldx, int M, float* const* Zs, float* const* As,
-                        const float* dY, float* d0, float* d1, float* dX, float S, cudaStream_t st, Fork* fork = nullptr) {
+                        const float* dY, float* d0, float* d1, float* dX, float S, cudaStream_t st, Fork* fork = nullptr,
+                        float* wt = nullptr) {
   const float* dz = dY;
   float* bufs[2] = {d0, d1};
   int which = 0;
@@ -101,8 +131,12 @@ static int mlp_backward(const Layer* L, int nl, const float* X, int64_t ldx, int
     }
     if (l > 0) {
       const bool has_act = L[l - 1].act >= 0;
-      CX_TRY(linear_backward_dx(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, bufs[which], L[l].in,
-                                has_act ? Zs[l - 1] : nullptr, L[l - 1].out, L[l - 1].act, S, st));
+      int on_tc = 0;
+      CX_TRY(dx_tensor(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, bufs[which], L[l].in, has_act ? Zs[l - 1] : nullptr,
+                       L[l - 1].out, L[l - 1].act, S, wt, st, &on_tc));
+      if (!on_tc)
+        CX_TRY(linear_backward_dx(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, bufs[which], L[l].in,
+                                  has_act ? Zs[l - 1] : nullptr, L[l - 1].out, L[l - 1].act, S, st));
       dz = bufs[which];
       which ^= 1;
     } else if (dX) {
@@ -154,6 +188,7 @@ struct ChainWs {
   float* d1;
   float* tmp0;
   float* tmp1;
+  float* wt;        // backward: one transposed weight matrix (the dX GEMM as X . W^T^T on the tensor cores)
 };
 
 static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backward, ChainWs& w) {
@@ -166,10 +201,12 @@ static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backw
     }
     w.d0 = ar.get<float>((size_t)M * maxw);
     w.d1 = ar.get<float>((size_t)M * maxw);
+    w.wt = ar.get<float>((size_t)maxw * maxw);
     w.tmp0 = w.tmp1 = nullptr;
   } else {
     w.tmp0 = ar.get<float>((size_t)M * maxw);
     w.tmp1 = ar.get<float>((size_t)M * maxw);
+    w.wt = nullptr;
   }
 }
 
@@ -249,7 +286,7 @@ int coordx_trunk_tc_supported(const coordx_net* net, int precision) {
 // per-layer GEMM chain in chunks of this many, so the workspace is bounded and the 3xTF32 tensor-core GEMM takes the
 // 256-wide layers (the fused FFMA kernel below is built for a few thousand axis samples)
 constexpr int64_t BRANCH_CHUNK = 65536;
-constexpr int64_t BRANCH_FUSED_MAX = 32768;
+constexpr int64_t BRANCH_FUSED_MAX = 255;     // from 256 rows on, the 128 x 64-tile 3xTF32 GEMM per layer beats the fused FFMA kernel
 
 size_t coordx_branch_workspace_bytes(const coordx_net* net, int branch, int64_t n, int backward) {
   if (check_net(net) != 0 || branch < 0 || branch >= net->n_branches) return 0;
@@ -300,7 +337,7 @@ int coordx_branch_backward(const coordx_net* net, int branch, const float* coord
   CX_TRY(mlp_forward(L, nl, coords, net->branch_in[branch], (int)n, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
   Fork* fork = nullptr;
   CX_TRY(get_fork(branch, &fork));
-  return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords, S, st, fork);
+  return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords, S, st, fork, w.wt);
 }
 
 // Training-mode pair: the forward keeps every layer's pre-activation / activation in `save` (the backward
@@ -317,7 +354,7 @@ int coordx_branch_forward_save(const coordx_net* net, int branch, const float* c
   ChainWs w{};
   carve_chain(ar, L, nl, n, true, w);
   if (!ar.ok() || !save) return set_err(COORDX_ERR_WORKSPACE, "branch forward (save): buffer too small%s (%lld < %lld)", "", (long long)save_bytes, (long long)ar.off);
-  if (bf::supported(net)) return bf::launch(net, branch, branch + 1, &coords, &n, &feat, st, w.Z, w.A);
+  if (bf::supported(net) && n <= BRANCH_FUSED_MAX) return bf::launch(net, branch, branch + 1, &coords, &n, &feat, st, w.Z, w.A);
   return mlp_forward(L, nl, coords, net->branch_in[branch], (int)n, feat, w.Z, w.A, nullptr, nullptr, 30.f * net->act_scale, st);
 }
 
@@ -337,7 +374,7 @@ int coordx_branch_backward_saved(const coordx_net* net, int branch, const float*
   Fork* fork = nullptr;
   CX_TRY(get_fork(branch, &fork));
   return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords,
-                      30.f * net->act_scale, st, fork);
+                      30.f * net->act_scale, st, fork, w.wt);
 }
 
 // -------------------------------------------------------------------------- trunk
@@ -453,7 +490,7 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
       fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, H0);
       CX_LAUNCH_CHECK();
       CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
-      CX_TRY(mlp_backward(L, nl, H0, net->hidden, (int)pts, w.Z, w.A, dY, w.d0, w.d1, dH0, S, st));
+      CX_TRY(mlp_backward(L, nl, H0, net->hidden, (int)pts, w.Z, w.A, dY, w.d0, w.d1, dH0, S, st, nullptr, w.wt));
       dh = dH0;
     }
     for (int b = 0; b < C; ++b) {
@@ -540,7 +577,9 @@ int coordx_infer_grid_host(const coordx_net* net, const float* const* coords_hos
   if (!ar.ok() || !dout) return set_err(COORDX_ERR_WORKSPACE, "infer_grid_host: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
   for (int c = 0; c < C; ++c)
     CX_CUDA(cudaMemcpyAsync(dcoords[c], coords_host[c], (size_t)n[c] * net->branch_in[c] * 4, cudaMemcpyHostToDevice, st));
-  if (bf::supported(net)) {                          // every branch in ONE launch (two CTAs per SM run side by side)
+  bool small = true;
+  for (int c = 0; c < C; ++c) small = small && n[c] <= BRANCH_FUSED_MAX;
+  if (bf::supported(net) && small) {                 // every branch in ONE launch (two CTAs per SM run side by side)
     CX_TRY(bf::launch(net, 0, C, dcoords, n, dfeat, st));
   } else {
     for (int c = 0; c < C; ++c) CX_TRY(coordx_branch_forward(net, c, dcoords[c], n[c], dfeat[c], scratch, sws, stream));

@@ -12,7 +12,9 @@
 // ~10x the FFMA kernel's throughput on the large per-axis GEMMs: the 262 144 x 1024 x 1024 layers of the video net's
 // xy branch, the U/V tables and the output GEMM of the separable sum path.
 //
-// One 128 x 256 output tile per CTA, K in chunks of 32 (= one 128-byte SWIZZLE_128B row of fp32).  No operand image
+// One 128 x BN output tile per CTA (BN = 256 for the large GEMMs; BN = 64 for the per-axis branch layers, M = a few
+// thousand rows and N = 256, so that they spread over 4x more SMs), K in chunks of 32 (= one 128-byte SWIZZLE_128B
+// row of fp32).  No operand image
 // in global memory and no TMA descriptor: 8 producer warps read X and W rows with coalesced 16-byte loads (one chunk
 // ahead, in registers), split hi/lo and store the four K-major tiles (A_hi, A_lo, B_hi, B_lo: 96 KB per stage, 2
 // stages); one elected thread issues 12 kind::tf32 MMAs (M128 x N256 x K8) per chunk; the producer warps drain the
@@ -24,13 +26,18 @@
 namespace coordx {
 namespace g3 {
 
-constexpr int BM = 128, BN = 256, BK = 32;
-constexpr uint32_t A_T = BM * 128, B_T = BN * 128;       // 16 KB, 32 KB: [rows x 128 B] SWIZZLE_128B
-constexpr uint32_t STAGE = 2 * A_T + 2 * B_T;            // A_hi | A_lo | B_hi | B_lo
+constexpr int BM = 128, BK = 32;
+constexpr uint32_t A_T = BM * 128;                       // 16 KB: [rows x 128 B] SWIZZLE_128B
 constexpr int STAGES = 2;
-constexpr uint32_t SM_BAR = STAGES * STAGE;
-constexpr uint32_t SM_TOTAL = SM_BAR + 128;
 constexpr int THREADS = 9 * 32;                          // 8 producer / epilogue warps + the MMA issuer
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t B_T = BN * 128;              // 32 KB (BN 256) / 8 KB (BN 64)
+  static constexpr uint32_t STAGE = 2 * A_T + 2 * B_T;   // A_hi | A_lo | B_hi | B_lo
+  static constexpr uint32_t SM_BAR = STAGES * STAGE;
+  static constexpr uint32_t SM_TOTAL = SM_BAR + 128;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;          // main + cross-term accumulator (power of two >= 32)
+};
 
 struct Args {
   const float* A;      // X [M, K], row stride lda (16-byte aligned rows)
@@ -44,6 +51,8 @@ struct Args {
   float bscale;
   int act;             // COORDX_ACT_* or -1
   float S;
+  const float* zprev;  // dX form (nullable): the result is multiplied by act'(zprev[m * ldz + n]) and stored to Y
+  int64_t ldz;
 };
 
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -71,8 +80,10 @@ __device__ __forceinline__ void split_store(uint8_t* hi_tile, uint8_t* lo_tile, 
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
+template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const Args g) {
+  constexpr uint32_t B_T = Cfg<BN>::B_T, STAGE = Cfg<BN>::STAGE, SM_BAR = Cfg<BN>::SM_BAR, TMEM_COLS = Cfg<BN>::TMEM_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
@@ -95,7 +106,7 @@ gemm_tf32x3_kernel(const Args g) {
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(b_slot, 512);
+    ptx::tmem_alloc(b_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -116,8 +127,8 @@ gemm_tf32x3_kernel(const Args g) {
         for (int ks = 0; ks < 4; ++ks) {             // 8 tf32 = 32 bytes per K-step
           const uint64_t dah = ptx::umma_desc_k_sw128(a_hi + ks * 32), dal = ptx::umma_desc_k_sw128(a_lo + ks * 32);
           const uint64_t dbh = ptx::umma_desc_k_sw128(b_hi + ks * 32), dbl = ptx::umma_desc_k_sw128(b_lo + ks * 32);
-          mma_tf32_ss(tacc + 256, dal, dbh, idesc, (kc | ks) != 0);      // cross terms: their own accumulator
-          mma_tf32_ss(tacc + 256, dah, dbl, idesc, 1);
+          mma_tf32_ss(tacc + BN, dal, dbh, idesc, (kc | ks) != 0);      // cross terms: their own accumulator
+          mma_tf32_ss(tacc + BN, dah, dbl, idesc, 1);
           mma_tf32_ss(tacc, dah, dbh, idesc, (kc | ks) != 0);
         }
         ptx::mma_commit(b_empty + 8 * s);
@@ -129,39 +140,46 @@ gemm_tf32x3_kernel(const Args g) {
     // ============================ producers ============================
     const int tid = threadIdx.x;                     // 0..255
     const int piece = tid & 7, rbase = tid >> 3;     // 16-byte piece of the 128-byte row; rows rbase + 32 i
-    float4 ra[4], rb[8];
-    auto gload = [&](int kc) {
+    // two register sets: the global loads of chunk kc + 2 are issued right after chunk kc has been written to shared
+    // memory and are not needed before chunk kc + 1 has been written too - a whole chunk period to cover the L2 latency
+    float4 ra[2][4], rb[2][BN / 32];
+    auto gload = [&](int set, int kc) {
       const int k0 = kc * BK + piece * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + rbase + 32 * i;
-        ra[i] = m < g.M ? __ldg(reinterpret_cast<const float4*>(g.A + (int64_t)m * g.lda + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ra[set][i] = m < g.M ? __ldg(reinterpret_cast<const float4*>(g.A + (int64_t)m * g.lda + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < BN / 32; ++i) {
         const int n = n0 + rbase + 32 * i;
-        rb[i] = n < g.N ? __ldg(reinterpret_cast<const float4*>(g.B + (int64_t)n * g.ldb + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[set][i] = n < g.N ? __ldg(reinterpret_cast<const float4*>(g.B + (int64_t)n * g.ldb + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    gload(0);
-    for (int kc = 0; kc < nk; ++kc) {
+    auto produce = [&](int set, int kc) {
       const int s = kc & 1;
       ptx::mbar_wait(b_empty + 8 * s, ((kc >> 1) & 1) ^ 1);
       uint8_t* st = smem_gen + s * STAGE;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = rbase + 32 * i;
-        split_store(st, st + A_T, (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4), ra[i]);
+        split_store(st, st + A_T, (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4), ra[set][i]);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < BN / 32; ++i) {
         const int row = rbase + 32 * i;
-        split_store(st + 2 * A_T, st + 2 * A_T + B_T, (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4), rb[i]);
+        split_store(st + 2 * A_T, st + 2 * A_T + B_T, (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4), rb[set][i]);
       }
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(b_full + 8 * s);
-      if (kc + 1 < nk) gload(kc + 1);
+      if (kc + 2 < nk) gload(set, kc + 2);
+    };
+    gload(0, 0);
+    if (nk > 1) gload(1, 1);
+    for (int kc = 0; kc < nk; kc += 2) {
+      produce(0, kc);
+      if (kc + 1 < nk) produce(1, kc + 1);
     }
     // ============================ epilogue ============================
     ptx::mbar_wait(b_acc, 0);
@@ -171,18 +189,23 @@ gemm_tf32x3_kernel(const Args g) {
     const float add1 = g.bias1 ? __ldg(g.bias1) : 0.f;
     const bool vec = g.cs == 1 && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.Y) | reinterpret_cast<uintptr_t>(g.Z)) & 15) == 0;
 #pragma unroll 1
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < BN / 64; ++b) {                  // this warp: lane quadrant q, column half `half`
       uint32_t r[32], r2[32];
-      ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + half * 128 + b * 32, r);
-      ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + 256 + half * 128 + b * 32, r2);
+      ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + half * (BN / 2) + b * 32, r);
+      ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + BN + half * (BN / 2) + b * 32, r2);
       ptx::tmem_ld_wait();
-      const int nb = n0 + half * 128 + b * 32;
+      const int nb = n0 + half * (BN / 2) + b * 32;
       if (m < g.M && nb < g.N) {
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int n = nb + i;
           v[i] = (__uint_as_float(r[i]) + __uint_as_float(r2[i])) + add1 + ((g.bias && n < g.N) ? __ldg(g.bias + n) * g.bscale : 0.f);
+        }
+        if (g.zprev) {                                  // dX = (dZ W) * act'(Zprev)
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < g.N) v[i] *= act_grad(g.act, g.S, __ldg(g.zprev + (int64_t)m * g.ldz + nb + i));
         }
         if (vec && nb + 32 <= g.N) {
           if (g.Z) {
@@ -191,7 +214,7 @@ gemm_tf32x3_kernel(const Args g) {
             for (int i = 0; i < 8; ++i) z[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
           if (g.Y) {
-            if (g.act >= 0) {
+            if (g.act >= 0 && !g.zprev) {
 #pragma unroll 1
               for (int i = 0; i < 32; ++i) v[i] = act_fwd(g.act, g.S, v[i]);
             }
@@ -205,7 +228,7 @@ gemm_tf32x3_kernel(const Args g) {
             const int n = nb + i;
             if (n >= g.N) break;
             if (g.Z) g.Z[(int64_t)m * g.ldc + (int64_t)n * g.cs] = v[i];
-            if (g.Y) g.Y[(int64_t)m * g.ldc + (int64_t)n * g.cs] = g.act < 0 ? v[i] : act_fwd(g.act, g.S, v[i]);
+            if (g.Y) g.Y[(int64_t)m * g.ldc + (int64_t)n * g.cs] = (g.act < 0 || g.zprev) ? v[i] : act_fwd(g.act, g.S, v[i]);
           }
         }
       }
@@ -216,32 +239,44 @@ gemm_tf32x3_kernel(const Args g) {
   __syncthreads();
   if (warp == W_MMA) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tacc, 512);
+    ptx::tmem_dealloc(tacc, TMEM_COLS);
   }
 }
 
-// worth it (and legal) for this problem?  Large enough to fill the chip with 128 x 256 tiles, K a multiple of 32,
-// 16-byte aligned operand rows.  COORDX_FP32_GEMM=ffma forces the FFMA kernel.
-static bool usable(const Args& a) {
+// worth it (and legal) for this problem?  K a multiple of 32, 16-byte aligned operand rows, and enough work: the
+// 128 x 256 tile for GEMMs that fill the chip with it, the 128 x 64 tile for the per-axis layers (M >= 256 rows).
+// Returns the N tile width to use, 0 = take the FFMA kernel.  COORDX_FP32_GEMM=ffma forces the FFMA kernel.
+static int tile_n(const Args& a) {
   const char* e = getenv("COORDX_FP32_GEMM");
-  if (e && strcmp(e, "ffma") == 0) return false;
-  if (a.K < BK || a.K % BK != 0 || a.N < 128) return false;
-  if ((a.lda & 3) || (a.ldb & 3)) return false;
-  if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return false;
-  const int64_t tiles = cdiv(a.M, BM) * cdiv(a.N, BN);
-  return tiles >= 32 && (int64_t)a.M * a.N * a.K >= ((int64_t)1 << 28);
+  if (e && strcmp(e, "ffma") == 0) return 0;
+  if (a.K < BK || a.K % BK != 0 || a.N < 64) return 0;
+  // ReLU layers stay on the FFMA kernel: its pre-activations differ from the reference's by ~1e-7 relative, the 3xTF32
+  // ones by ~2e-6, and every pre-activation that changes sign flips a ReLU gate (a 1/P-sized jump in the gradients)
+  if (a.act == COORDX_ACT_RELU && !a.zprev) return 0;
+  if ((a.lda & 3) || (a.ldb & 3)) return 0;
+  if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return 0;
+  const int64_t work = (int64_t)a.M * a.N * a.K;
+  if (a.N >= 128 && cdiv(a.M, BM) * cdiv(a.N, 256) >= 32 && work >= ((int64_t)1 << 28)) return 256;
+  if (a.M >= 256 && a.K >= 128 && work >= ((int64_t)1 << 24)) return 64;
+  return 0;
 }
+static bool usable(const Args& a) { return tile_n(a) != 0; }
 
-static int launch(const Args& a, cudaStream_t st) {
+template <int BN>
+static int launch_bn(const Args& a, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+    CX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SM_TOTAL));
     attr_done = true;
   }
   dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, BM));
-  gemm_tf32x3_kernel<<<grid, THREADS, SM_TOTAL, st>>>(a);
+  gemm_tf32x3_kernel<BN><<<grid, THREADS, Cfg<BN>::SM_TOTAL, st>>>(a);
   CX_LAUNCH_CHECK();
   return 0;
+}
+
+static int launch(const Args& a, cudaStream_t st) {
+  return tile_n(a) == 256 ? launch_bn<256>(a, st) : launch_bn<64>(a, st);
 }
 
 }  // namespace g3
