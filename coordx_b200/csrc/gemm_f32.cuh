@@ -243,9 +243,41 @@ static int linear_forward(const float* X, int64_t ldx, const float* W, const flo
   return launch_sgemm<true, true, EPI_LINEAR>(g, st);
 }
 
+// Narrow input gradient (K <= 8: the coordinates of a branch, f_c = 1..3 without positional encoding): one warp per row.
+// dX[m, k] = sum_n dZ[m, n] W[n, k]
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+dx_narrow_kernel(const float* __restrict__ dZ, int64_t lddz, const float* __restrict__ W, int M, int N, int K,
+                 float* __restrict__ dX, int64_t lddx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  const float* dz = dZ + (int64_t)warp * lddz;
+  for (int n = lane; n < N; n += 32) {
+    const float d = dz[n];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) acc[k] = fmaf(d, W[(int64_t)n * K + k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && k < K) dX[(int64_t)warp * lddx + k] = v;
+  }
+}
+
 // dX[M,K] = dZ[M,N] W[N,K], optionally * act'(Zprev[M,K])
 static int linear_backward_dx(const float* dZ, int64_t lddz, const float* W, int M, int N, int K, float* dX, int64_t lddx,
                               const float* Zprev, int64_t ldz, int act, float S, cudaStream_t st) {
+  if (K <= 8 && !Zprev && M > 0) {
+    dx_narrow_kernel<8><<<(unsigned)cdiv((int64_t)M * 32, 256), 256, 0, st>>>(dZ, lddz, W, M, N, K, dX, lddx);
+    CX_LAUNCH_CHECK();
+    return 0;
+  }
   GemmArgs g{};
   g.A = dZ; g.lda = lddz; g.B = W; g.ldb = K; g.M = M; g.N = K; g.K = N;
   g.Y = dX; g.ldc = lddx; g.Zprev = Zprev; g.ldz = ldz; g.act = act; g.S = S;

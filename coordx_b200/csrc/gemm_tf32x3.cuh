@@ -66,6 +66,11 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+__device__ __forceinline__ float act_fwd_inl(int act, float S, float z) { return act == COORDX_ACT_SINE ? sinf(S * z) : fmaxf(z, 0.f); }
+__device__ __forceinline__ float act_grad_inl(int act, float S, float z) {
+  return act == COORDX_ACT_SINE ? S * cosf(S * z) : (z > 0.f ? 1.f : 0.f);
+}
+
 __device__ __forceinline__ float rn_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -202,10 +207,26 @@ gemm_tf32x3_kernel(const Args g) {
           const int n = nb + i;
           v[i] = (__uint_as_float(r[i]) + __uint_as_float(r2[i])) + add1 + ((g.bias && n < g.N) ? __ldg(g.bias + n) * g.bscale : 0.f);
         }
+        // activations: inlined and fully unrolled on purpose - the accurate sinf / cosf is a ~30-instruction dependent
+        // chain, and with 2 warps per scheduler a rolled loop of calls ran one chain at a time (6 us of a 16 us launch)
         if (g.zprev) {                                  // dX = (dZ W) * act'(Zprev)
-#pragma unroll 1
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < g.N) v[i] *= act_grad(g.act, g.S, __ldg(g.zprev + (int64_t)m * g.ldz + nb + i));
+          const float* zp = g.zprev + (int64_t)m * g.ldz + nb;
+          if (nb + 32 <= g.N && (g.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.zprev) & 15) == 0) {
+            float4 z4[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z4[i] = __ldg(reinterpret_cast<const float4*>(zp) + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i + 0] *= act_grad_inl(g.act, g.S, z4[i].x);
+              v[4 * i + 1] *= act_grad_inl(g.act, g.S, z4[i].y);
+              v[4 * i + 2] *= act_grad_inl(g.act, g.S, z4[i].z);
+              v[4 * i + 3] *= act_grad_inl(g.act, g.S, z4[i].w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < g.N) v[i] *= act_grad(g.act, g.S, __ldg(zp + i));
+          }
         }
         if (vec && nb + 32 <= g.N) {
           if (g.Z) {
@@ -215,20 +236,21 @@ gemm_tf32x3_kernel(const Args g) {
           }
           if (g.Y) {
             if (g.act >= 0 && !g.zprev) {
-#pragma unroll 1
-              for (int i = 0; i < 32; ++i) v[i] = act_fwd(g.act, g.S, v[i]);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = act_fwd_inl(g.act, g.S, v[i]);
             }
             float4* y = reinterpret_cast<float4*>(g.Y + (int64_t)m * g.ldc + nb);
 #pragma unroll
             for (int i = 0; i < 8; ++i) y[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
         } else {
-#pragma unroll 1
-          for (int i = 0; i < 32; ++i) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {                 // (static indices: v[] stays in registers)
             const int n = nb + i;
-            if (n >= g.N) break;
-            if (g.Z) g.Z[(int64_t)m * g.ldc + (int64_t)n * g.cs] = v[i];
-            if (g.Y) g.Y[(int64_t)m * g.ldc + (int64_t)n * g.cs] = (g.act < 0 || g.zprev) ? v[i] : act_fwd(g.act, g.S, v[i]);
+            if (n < g.N) {
+              if (g.Z) g.Z[(int64_t)m * g.ldc + (int64_t)n * g.cs] = v[i];
+              if (g.Y) g.Y[(int64_t)m * g.ldc + (int64_t)n * g.cs] = (g.act < 0 || g.zprev) ? v[i] : act_fwd(g.act, g.S, v[i]);
+            }
           }
         }
       }
