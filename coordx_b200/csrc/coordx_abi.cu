@@ -547,7 +547,7 @@ size_t coordx_infer_grid_host_workspace_bytes(const coordx_net* net, const int64
   size_t bws = 0;
   for (int c = 0; c < net->n_branches; ++c) bws = max(bws, coordx_branch_workspace_bytes(net, c, n[c], 0));
   const size_t tws = coordx_trunk_workspace_bytes(net, n, 0, n[0], precision, 0);
-  total += align_up(max(bws, tws), 256);
+  total += align_up(max((size_t)net->n_branches * align_up(bws, 256), tws), 256);
   total += align_up((size_t)P * net->layer_out[net->n_layers - 1] * 4, 256);   // out
   return total + 1024;
 }
@@ -570,7 +570,7 @@ int coordx_infer_grid_host(const coordx_net* net, const float* const* coords_hos
   size_t bws = 0;
   for (int c = 0; c < C; ++c) bws = max(bws, coordx_branch_workspace_bytes(net, c, n[c], 0));
   const size_t tws = coordx_trunk_workspace_bytes(net, n, 0, n[0], precision, 0);
-  const size_t sws = max(bws, tws);
+  const size_t sws = max((size_t)net->n_branches * align_up(bws, 256), tws);
   char* scratch = ar.get<char>(sws);
   const int ow = net->layer_out[net->n_layers - 1];
   float* dout = ar.get<float>((size_t)P * ow);
@@ -581,6 +581,19 @@ int coordx_infer_grid_host(const coordx_net* net, const float* const* coords_hos
   for (int c = 0; c < C; ++c) small = small && n[c] <= BRANCH_FUSED_MAX;
   if (bf::supported(net) && small) {                 // every branch in ONE launch (two CTAs per SM run side by side)
     CX_TRY(bf::launch(net, 0, C, dcoords, n, dfeat, st));
+  } else if (C > 1 && (size_t)C * align_up(bws, 256) <= sws) {
+    // per-layer chains: the branches are independent, one internal side stream each (fork / join with events),
+    // every branch with its own slice of the scratch area
+    Fork* fk[COORDX_MAX_BRANCHES];
+    for (int c = 1; c < C; ++c) CX_TRY(get_fork(c, &fk[c]));
+    CX_CUDA(cudaEventRecord(fk[1]->ev_main[0], st));                  // the coordinates are on the device
+    for (int c = 1; c < C; ++c) {
+      CX_CUDA(cudaStreamWaitEvent(fk[c]->side, fk[1]->ev_main[0], 0));
+      CX_TRY(coordx_branch_forward(net, c, dcoords[c], n[c], dfeat[c], scratch + c * align_up(bws, 256), bws, fk[c]->side));
+      CX_CUDA(cudaEventRecord(fk[c]->ev_side[0], fk[c]->side));
+    }
+    CX_TRY(coordx_branch_forward(net, 0, dcoords[0], n[0], dfeat[0], scratch, bws, stream));
+    for (int c = 1; c < C; ++c) CX_CUDA(cudaStreamWaitEvent(st, fk[c]->ev_side[0], 0));
   } else {
     for (int c = 0; c < C; ++c) CX_TRY(coordx_branch_forward(net, c, dcoords[c], n[c], dfeat[c], scratch, sws, stream));
   }

@@ -496,6 +496,25 @@ class SplitFCBlock(nn.Module):
         hs = list(hs)
         plan = _broadcast_axes([tuple(h.shape[:-1]) for h in hs])
         if plan is None:
+            leads = {tuple(h.shape[:-1]) for h in hs}
+            if len(leads) == 1 and len(hs) >= 1 and hs[0].is_cuda and hs[0].numel() > 0:
+                # Same leading shape everywhere = per-point features, no broadcast: the interpolated branch features
+                # of the rendering path (ray_rendering.py:139-144 hands forward_split_fusion a stacked [C, .., Hd]
+                # tensor).  One elementwise pass fuses them; the trunk then sees a 1 x P grid whose first axis is
+                # the fusion's neutral element, i.e. the same kernels as the grid (see _forward_scattered_fused).
+                h = hs[0]
+                for hi in hs[1:]:
+                    h = h + hi if self.fusion_operator == 'sum' else h * hi
+                lead = h.shape[:-1]
+                h2 = h.reshape(-1, h.shape[-1])
+                neutral = (torch.zeros if self.fusion_operator == 'sum' else torch.ones)(1, h2.shape[-1], dtype=h2.dtype,
+                                                                                        device=h2.device)
+                params = self.abi_params()
+                if _needs_grad([h2, *params]):
+                    out = _FusionFn.apply(self, precision, 2, neutral, h2, *params)
+                else:
+                    out = _fusion_forward(self, precision, [neutral, h2], params)[0]
+                return out.reshape(*lead, out.shape[-1])
             return self._fusion_eager(hs)
         order, ns, out_lead = plan
         feats = [hs[i].reshape(-1, hs[i].shape[-1]) for i in order]
