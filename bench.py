@@ -141,7 +141,7 @@ def main():
     ap.add_argument('--precision', default='bf16')
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--train-steps', type=int, default=5)
+    ap.add_argument('--train-steps', type=int, default=10)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -219,11 +219,16 @@ def main():
             e1.record()
             evs.append((e0, e1))
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
+        per = [a.elapsed_time(b) for a, b in evs]
+        ms = sum(per)
+        if max(per) > 3 * statistics.median(per):            # diagnostics only (stderr): an outlier inside the timed region
+            print(f'[bench rank {rank}] uneven steps (ms): ' + ' '.join(f'{v:.2f}' for v in per), file=sys.stderr, flush=True)
+        med = statistics.median(per) * len(per)
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms, med], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            ms, med = float(t[0].item()), float(t[1].item())
+        timed.last_median_total = med                         # K x the median step (max over ranks): robust to one stalled step
         return ms
 
     sampler = ClockSampler(local_rank)
@@ -311,10 +316,11 @@ def main():
         gt_host = gt.cpu().pin_memory()
         opt = torch.optim.Adam(lr=1e-4, params=model.parameters(), fused=True)     # training.py:17 (fused = implementation detail)
         xs, ys = x.reshape(1, H, 1, 1), y.reshape(1, 1, W, 1)
+        from coordx_b200 import loss_functions as LF
 
         def train_step(gtd=gt):
-            out = model({'coords_split': [xs, ys]})['model_out']
-            loss = ((out - gtd) ** 2).mean()
+            mo = model({'coords_split': [xs, ys]})
+            loss = LF.image_mse(None, mo, {'img': gtd})['img_loss']          # loss_functions.py:8-12 (drop-in module)
             opt.zero_grad()
             loss.backward()
             if world > 1:
@@ -322,7 +328,13 @@ def main():
                 sharding.allreduce_grads(model.parameters(), world)
             opt.step()
             return loss
-        tr_ms = timed(train_step, args.train_steps, 3)
+        if world > 1:                                         # NCCL sets its channels up lazily: not inside the timed region
+            from coordx_b200 import sharding
+            warm = torch.zeros(sum(p.numel() for p in model.parameters()), device=dev)
+            for _ in range(3):
+                dist.all_reduce(warm)
+        tr_ms_sum = timed(train_step, args.train_steps, 5)
+        tr_ms = timed.last_median_total
         loss_host = torch.empty(1).pin_memory()
 
         def train_e2e():
@@ -337,12 +349,14 @@ def main():
             # the same iteration (fwd + MSE + bwd + Adam) replayed from ONE CUDA graph (runtime.CapturedTrainStep)
             from coordx_b200.runtime import CapturedTrainStep
             cap = CapturedTrainStep(model, [xs, ys], gt, loss='mse', lr=1e-4)
-            g_ms = timed(cap.replay, args.train_steps, 3) / args.train_steps
+            timed(cap.replay, args.train_steps, 3)
+            g_ms = timed.last_median_total / args.train_steps
             graph_it_s = 1e3 / g_ms
             best_ms = min(best_ms, g_ms)
             del cap
         train = {'metric': 'train iters/sec', 'value': 1e3 / best_ms, 'ms_per_iter': best_ms,
-                 'eager_value': eager_it_s, 'graph_value': graph_it_s,
+                 'eager_value': eager_it_s, 'graph_value': graph_it_s, 'eager_mean_ms_per_iter': tr_ms_sum / args.train_steps,
+                 'timing': 'per-iteration CUDA events, MEDIAN iteration x count (max over ranks); eager_mean_ms_per_iter is the plain mean',
                  'e2e_value': args.train_steps / (tr_e2e_ms * 1e-3),
                  'tflops_algorithmic': 3 * F / (best_ms * 1e-3) / 1e12,
                  'frac_of_sustained_peak': 3 * F / (best_ms * 1e-3) / 1e12 / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
