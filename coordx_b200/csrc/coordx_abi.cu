@@ -79,9 +79,14 @@ struct Fork {
   cudaEvent_t ev_side[COORDX_MAX_LAYERS + 2] = {};
 };
 
+// (one set per device and slot, created on first use - i.e. during the warm-up iterations that precede a graph
+//  capture; calls are expected from one host thread per device, like every other entry point of this library)
 static int get_fork(int slot, Fork** out) {
-  static Fork forks[COORDX_MAX_BRANCHES];
-  Fork& f = forks[slot % COORDX_MAX_BRANCHES];
+  constexpr int MAX_DEV = 16;
+  static Fork forks[MAX_DEV][COORDX_MAX_BRANCHES];
+  int dev = 0;
+  CX_CUDA(cudaGetDevice(&dev));
+  Fork& f = forks[dev % MAX_DEV][slot % COORDX_MAX_BRANCHES];
   if (!f.side) {
     CX_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
     for (int i = 0; i < COORDX_MAX_LAYERS + 2; ++i) {
@@ -530,6 +535,33 @@ int coordx_adam_step(float* param, const float* grad, float* exp_avg, float* exp
   const double bc2 = 1.0 - pow((double)beta2, (double)step_host);
   adam_kernel<<<(unsigned)cdiv(numel, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, numel, (float)(lr / bc1),
                                                                           beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), grad_scale_dev);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+int coordx_optim_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const int64_t* numel, float* state, float beta1, float beta2, float eps,
+                      float max_grad_norm, float lr_gamma, void* stream) {
+  if (n_tensors < 0 || n_tensors > COORDX_OPT_MAX_TENSORS) return set_err(COORDX_ERR_ARG, "optim_step: too many tensors%s (%lld)", "", n_tensors);
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel || !state) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (n_tensors == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  OptimTensors t{};
+  t.n = n_tensors;
+  int64_t biggest = 1;
+  for (int k = 0; k < n_tensors; ++k) {
+    if (!params[k] || !grads[k] || !exp_avg[k] || !exp_avg_sq[k] || numel[k] < 0) return set_err(COORDX_ERR_ARG, "optim_step: bad tensor%s (%lld)", "", k);
+    t.p[k] = params[k]; t.g[k] = grads[k]; t.m[k] = exp_avg[k]; t.v[k] = exp_avg_sq[k]; t.numel[k] = numel[k];
+    biggest = max(biggest, numel[k]);
+  }
+  dim3 grid((unsigned)min((int64_t)64, cdiv(biggest, 256 * 4)), (unsigned)n_tensors);
+  if (max_grad_norm > 0.f) {
+    optim_sqnorm_kernel<<<grid, 256, 0, st>>>(t, state);
+    CX_LAUNCH_CHECK();
+  }
+  optim_adam_kernel<<<grid, 256, 0, st>>>(t, state, beta1, beta2, eps, max_grad_norm);
+  CX_LAUNCH_CHECK();
+  optim_advance_kernel<<<1, 1, 0, st>>>(state, lr_gamma);
   CX_LAUNCH_CHECK();
   return 0;
 }

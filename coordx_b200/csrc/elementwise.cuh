@@ -147,4 +147,60 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] -= step_size * (mi / denom);
 }
 
+// ---- the whole optimiser step of training.py:140-146 over a LIST of tensors, state on the device -----------------
+// (clip_grad_norm_ coefficient, Adam for every parameter tensor, step counter and ExponentialLR decay): three small
+// launches per iteration, replayable from a CUDA graph because nothing depends on a host-side step count.
+struct OptimTensors {
+  int n;
+  float* p[COORDX_OPT_MAX_TENSORS];
+  const float* g[COORDX_OPT_MAX_TENSORS];
+  float* m[COORDX_OPT_MAX_TENSORS];
+  float* v[COORDX_OPT_MAX_TENSORS];
+  int64_t numel[COORDX_OPT_MAX_TENSORS];
+};
+
+// state[0] = lr, state[1] = step (as float, exact up to 2^24), state[2] = sum of squared gradients, state[3] = clip coef
+__global__ void __launch_bounds__(256) optim_sqnorm_kernel(OptimTensors t, float* __restrict__ state) {
+  const int k = blockIdx.y;
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < t.numel[k]; i += (int64_t)gridDim.x * 256) {
+    const float gi = t.g[k][i];
+    s += gi * gi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float r = 0.f;
+    for (int w = 0; w < 8; ++w) r += red[w];
+    if (r != 0.f) atomicAdd(&state[2], r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+optim_adam_kernel(OptimTensors t, const float* __restrict__ state, float beta1, float beta2, float eps, float max_norm) {
+  const int k = blockIdx.y;
+  const float lr = state[0], step = state[1] + 1.f;
+  // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+  const float coef = max_norm > 0.f ? fminf(max_norm / (sqrtf(state[2]) + 1e-6f), 1.f) : 1.f;
+  const float bc1 = 1.f - powf(beta1, step), bc2 = 1.f - powf(beta2, step);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < t.numel[k]; i += (int64_t)gridDim.x * 256) {
+    const float gi = t.g[k][i] * coef;
+    const float mi = beta1 * t.m[k][i] + (1.f - beta1) * gi;
+    const float vi = beta2 * t.v[k][i] + (1.f - beta2) * gi * gi;
+    t.m[k][i] = mi;
+    t.v[k][i] = vi;
+    t.p[k][i] -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+  }
+}
+
+__global__ void optim_advance_kernel(float* __restrict__ state, float lr_gamma) {
+  state[0] *= lr_gamma;
+  state[1] += 1.f;
+  state[2] = 0.f;
+}
+
 }  // namespace coordx

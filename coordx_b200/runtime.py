@@ -95,6 +95,64 @@ def infer_grid_host(model: 'M.SingleBVPNet', coords_host: Sequence[torch.Tensor]
     return out_host
 
 
+class DeviceAdam:
+    """torch.optim.Adam with its defaults (training.py:17), optionally preceded by clip_grad_norm_(max_grad_norm)
+    (training.py:140-144) and followed by one ExponentialLR step (training.py:25,146), as ONE C call of three small
+    launches (`coordx_optim_step`): the step count and the learning rate live on the device, so the whole optimiser
+    step replays from a CUDA graph.  Differences from the torch objects it replaces: `p.grad` is read, not rescaled in
+    place, by the clipping; state is `exp_avg` / `exp_avg_sq` lists plus `state` = [lr, steps, scratch, -]."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0, lr_gamma=1.0):
+        self.params = [p for p in params if p.requires_grad]
+        if len(self.params) > 32:
+            raise ValueError('DeviceAdam: at most 32 parameter tensors (COORDX_OPT_MAX_TENSORS)')
+        if not all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self.params):
+            raise _lib.CoordxError('DeviceAdam: contiguous fp32 CUDA parameters required (no CPU path)')
+        dev = self.params[0].device
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.state = torch.tensor([float(lr), 0.0, 0.0, 0.0], dtype=torch.float32, device=dev)
+        self.betas, self.eps, self.max_grad_norm, self.lr_gamma = betas, float(eps), float(max_grad_norm), float(lr_gamma)
+        self._numel = _lib.i64_array([p.numel() for p in self.params])
+        self._fixed = [_lib.ptr_array([t.data_ptr() for t in ts]) for ts in (self.params, self.exp_avg, self.exp_avg_sq)]
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self):
+        ps = [(i, p) for i, p in enumerate(self.params) if p.grad is not None]
+        if not ps:
+            return
+        if len(ps) == len(self.params):
+            pp, mm, vv, nn = self._fixed[0], self._fixed[1], self._fixed[2], self._numel
+        else:                                        # a parameter without gradient this step is skipped, as torch does
+            pp = _lib.ptr_array([p.data_ptr() for _, p in ps])
+            mm = _lib.ptr_array([self.exp_avg[i].data_ptr() for i, _ in ps])
+            vv = _lib.ptr_array([self.exp_avg_sq[i].data_ptr() for i, _ in ps])
+            nn = _lib.i64_array([p.numel() for _, p in ps])
+        for _, p in ps:
+            if not (p.grad.is_contiguous() and p.grad.dtype == torch.float32):
+                p.grad = p.grad.contiguous().float()
+        gg = _lib.ptr_array([p.grad.data_ptr() for _, p in ps])
+        dev = self.state.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().coordx_optim_step(len(ps), pp, gg, mm, vv, nn, self.state.data_ptr(), self.betas[0],
+                                                     self.betas[1], self.eps, self.max_grad_norm, self.lr_gamma,
+                                                     torch.cuda.current_stream(dev).cuda_stream), 'coordx_optim_step')
+
+    def snapshot(self):
+        return [t.clone() for t in (*self.exp_avg, *self.exp_avg_sq, self.state)]
+
+    def restore(self, snap):
+        with torch.no_grad():
+            for t, s in zip((*self.exp_avg, *self.exp_avg_sq, self.state), snap):
+                t.copy_(s)
+
+
 class CapturedTrainStep:
     """CUDA-graph replay of ONE training iteration of training.py:112-146 for fixed shapes:
     model({'coords_split': ...}) -> loss -> backward -> [clip_grad_norm_ 1.0] -> Adam.step, i.e. the body of the
@@ -115,16 +173,21 @@ class CapturedTrainStep:
         self.static_gt = gt.detach().clone()
         self.clip_grad = clip_grad
         self.params = [p for p in model.parameters() if p.requires_grad]
-        # lr_gamma: the reference's ExponentialLR (training.py:25, stepped once per iteration :146) as a device-side
-        # schedule: the learning rate is a device scalar that the captured iteration itself decays
+        # Default optimiser: DeviceAdam - clip_grad_norm_ (if clip_grad), Adam and the reference's ExponentialLR
+        # (lr_gamma; training.py:25, stepped once per iteration :146) in one C call with device-side step / lr state.
+        # A caller-supplied torch optimiser must be capturable (and cannot take lr_gamma).
         self.lr_gamma = lr_gamma
-        self.lr_t = torch.tensor(float(lr), device=self.static_gt.device) if lr_gamma is not None else None
-        if lr_gamma is not None and optimizer is not None:
-            raise ValueError('lr_gamma needs the built-in optimizer (its learning rate is a device tensor)')
-        self.opt = optimizer or torch.optim.Adam(self.params, lr=self.lr_t if lr_gamma is not None else lr,
-                                                 capturable=True, fused=True)   # one multi-tensor kernel
-        if not all(g.get('capturable', False) for g in self.opt.param_groups):
-            raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
+        if optimizer is None:
+            self.opt = DeviceAdam(self.params, lr=lr, max_grad_norm=1.0 if clip_grad else 0.0,
+                                  lr_gamma=1.0 if lr_gamma is None else lr_gamma)
+            self._own_opt = True
+        else:
+            if lr_gamma is not None:
+                raise ValueError('lr_gamma needs the built-in optimizer (its learning rate is device state)')
+            if not all(g.get('capturable', False) for g in optimizer.param_groups):
+                raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
+            self.opt = optimizer
+            self._own_opt = False
         if callable(loss):
             self.loss_fn = loss
         elif loss in ('mse', 'bce'):                 # one kernel: value and d loss / d out (loss_functions.py)
@@ -133,8 +196,11 @@ class CapturedTrainStep:
         else:
             raise ValueError(f'unknown loss {loss!r}')
         saved_p = [p.detach().clone() for p in self.params]
-        saved_s = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()}
-                   for p in self.params}
+        if self._own_opt:
+            saved_s = self.opt.snapshot()
+        else:
+            saved_s = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()}
+                       for p in self.params}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -148,26 +214,25 @@ class CapturedTrainStep:
         with torch.cuda.graph(self.graph):
             self.static_loss = self._iteration()
         with torch.no_grad():                                    # undo the warm-up updates
-            if self.lr_t is not None:
-                self.lr_t.fill_(float(lr))
             for p, s in zip(self.params, saved_p):
                 p.copy_(s)
-            for p in self.params:
-                st, old = self.opt.state.get(p, {}), saved_s[id(p)]
-                for k, v in st.items():
-                    if torch.is_tensor(v):
-                        v.copy_(old[k]) if k in old else v.zero_()
+            if self._own_opt:
+                self.opt.restore(saved_s)
+            else:
+                for p in self.params:
+                    st, old = self.opt.state.get(p, {}), saved_s[id(p)]
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.copy_(old[k]) if k in old else v.zero_()
         torch.cuda.synchronize()
 
     def _iteration(self):
         out = self.model({'coords_split': self.static_coords})['model_out']
         loss = self.loss_fn(out, self.static_gt)
         loss.backward()
-        if self.clip_grad:
+        if self.clip_grad and not self._own_opt:                 # (DeviceAdam clips inside its step)
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=1.)
         self.opt.step()
-        if self.lr_t is not None:
-            self.lr_t.mul_(self.lr_gamma)
         return loss
 
     def set_batch(self, coords: Sequence[torch.Tensor] = None, gt: torch.Tensor = None) -> None:

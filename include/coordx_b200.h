@@ -148,6 +148,15 @@ int coordx_adam_step(float* param, const float* grad, float* exp_avg, float* exp
                      int64_t numel, float lr, float beta1, float beta2, float eps,
                      int64_t step_host, const float* grad_scale_dev, void* stream);
 
+/* ---- the whole optimiser step of training.py:140-146 for a LIST of parameter tensors, replayable from a CUDA graph:
+ * optional clip_grad_norm_(max_grad_norm) (training.py:140-144; <= 0: off), torch.optim.Adam defaults (:17,146) and
+ * the ExponentialLR decay (:25; lr_gamma = 1: constant).  `state` is 4 device floats owned by the caller:
+ * {lr, completed steps, scratch (must start at 0), unused}; the call leaves lr *= lr_gamma and steps += 1.            */
+#define COORDX_OPT_MAX_TENSORS 32
+int coordx_optim_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const int64_t* numel, float* state, float beta1, float beta2,
+                      float eps, float max_grad_norm, float lr_gamma, void* stream);
+
 /* ---- whole-path inference with HOST buffers (the reference's --speed_test loop,
  * train_img.py:125-135): copies the per-axis coordinates in, runs branch + trunk, copies
  * the [P, out_width] result out.  Weights stay resident on the device (model.cuda()).    */
