@@ -193,63 +193,57 @@ gemm_tf32x3_kernel(const Args g) {
     const int m = m0 + q * 32 + lane;
     const float add1 = g.bias1 ? __ldg(g.bias1) : 0.f;
     const bool vec = g.cs == 1 && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.Y) | reinterpret_cast<uintptr_t>(g.Z)) & 15) == 0;
+    // Rolled loop over groups of 8 columns (static indices inside a group): 8 independent sinf / cosf chains are enough
+    // to fill the issue slots of the 2 warps per scheduler, and the epilogue stays a few hundred instructions - these
+    // kernels mostly start with a cold instruction cache (short launches between L2-flushing phases).
+    const int ncol = BN / 2;                             // this warp: lane quadrant q, column half `half`
+    const bool zvec = g.zprev && (g.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.zprev) & 15) == 0;
 #pragma unroll 1
-    for (int b = 0; b < BN / 64; ++b) {                  // this warp: lane quadrant q, column half `half`
-      uint32_t r[32], r2[32];
-      ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + half * (BN / 2) + b * 32, r);
-      ptx::tmem_ld_32x32b_x32(tacc + ((uint32_t)(q * 32) << 16) + BN + half * (BN / 2) + b * 32, r2);
+    for (int c8 = 0; c8 < ncol; c8 += 8) {
+      uint32_t r[8], r2[8];
+      ptx::tmem_ld_32x32b_x8(tacc + ((uint32_t)(q * 32) << 16) + half * ncol + c8, r);
+      ptx::tmem_ld_32x32b_x8(tacc + ((uint32_t)(q * 32) << 16) + BN + half * ncol + c8, r2);
       ptx::tmem_ld_wait();
-      const int nb = n0 + half * (BN / 2) + b * 32;
+      const int nb = n0 + half * ncol + c8;
       if (m < g.M && nb < g.N) {
-        float v[32];
+        const bool full = nb + 8 <= g.N;
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = nb + i;
-          v[i] = (__uint_as_float(r[i]) + __uint_as_float(r2[i])) + add1 + ((g.bias && n < g.N) ? __ldg(g.bias + n) * g.bscale : 0.f);
-        }
-        // activations: inlined and fully unrolled on purpose - the accurate sinf / cosf is a ~30-instruction dependent
-        // chain, and with 2 warps per scheduler a rolled loop of calls ran one chain at a time (6 us of a 16 us launch)
+        for (int i = 0; i < 8; ++i)
+          v[i] = (__uint_as_float(r[i]) + __uint_as_float(r2[i])) + add1 + ((g.bias && nb + i < g.N) ? __ldg(g.bias + nb + i) * g.bscale : 0.f);
         if (g.zprev) {                                  // dX = (dZ W) * act'(Zprev)
           const float* zp = g.zprev + (int64_t)m * g.ldz + nb;
-          if (nb + 32 <= g.N && (g.ldz & 3) == 0 && (reinterpret_cast<uintptr_t>(g.zprev) & 15) == 0) {
-            float4 z4[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) z4[i] = __ldg(reinterpret_cast<const float4*>(zp) + i);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i + 0] *= act_grad_inl(g.act, g.S, z4[i].x);
-              v[4 * i + 1] *= act_grad_inl(g.act, g.S, z4[i].y);
-              v[4 * i + 2] *= act_grad_inl(g.act, g.S, z4[i].z);
-              v[4 * i + 3] *= act_grad_inl(g.act, g.S, z4[i].w);
-            }
+          float z[8];
+          if (zvec && full) {
+            const float4 z0 = __ldg(reinterpret_cast<const float4*>(zp)), z1 = __ldg(reinterpret_cast<const float4*>(zp) + 1);
+            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (nb + i < g.N) v[i] *= act_grad(g.act, g.S, __ldg(zp + i));
+            for (int i = 0; i < 8; ++i) z[i] = nb + i < g.N ? __ldg(zp + i) : 0.f;
           }
-        }
-        if (vec && nb + 32 <= g.N) {
-          if (g.Z) {
-            float4* z = reinterpret_cast<float4*>(g.Z + (int64_t)m * g.ldc + nb);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) v[i] *= act_grad_inl(g.act, g.S, z[i]);
+        }
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = (g.act >= 0 && !g.zprev && g.Y) ? act_fwd_inl(g.act, g.S, v[i]) : v[i];
+        if (vec && full) {
+          if (g.Z) {
+            float4* zo = reinterpret_cast<float4*>(g.Z + (int64_t)m * g.ldc + nb);
+            zo[0] = make_float4(v[0], v[1], v[2], v[3]);
+            zo[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
           if (g.Y) {
-            if (g.act >= 0 && !g.zprev) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = act_fwd_inl(g.act, g.S, v[i]);
-            }
-            float4* y = reinterpret_cast<float4*>(g.Y + (int64_t)m * g.ldc + nb);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            float4* yo = reinterpret_cast<float4*>(g.Y + (int64_t)m * g.ldc + nb);
+            yo[0] = make_float4(y[0], y[1], y[2], y[3]);
+            yo[1] = make_float4(y[4], y[5], y[6], y[7]);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {                 // (static indices: v[] stays in registers)
-            const int n = nb + i;
-            if (n < g.N) {
-              if (g.Z) g.Z[(int64_t)m * g.ldc + (int64_t)n * g.cs] = v[i];
-              if (g.Y) g.Y[(int64_t)m * g.ldc + (int64_t)n * g.cs] = (g.act < 0 || g.zprev) ? v[i] : act_fwd(g.act, g.S, v[i]);
+          for (int i = 0; i < 8; ++i) {                  // (static indices: the arrays stay in registers)
+            if (nb + i < g.N) {
+              if (g.Z) g.Z[(int64_t)m * g.ldc + (int64_t)(nb + i) * g.cs] = v[i];
+              if (g.Y) g.Y[(int64_t)m * g.ldc + (int64_t)(nb + i) * g.cs] = y[i];
             }
           }
         }
