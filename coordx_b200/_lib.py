@@ -93,6 +93,7 @@ SIGNATURES = {
                                    C.c_float, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]),
     'coordx_optim_step': (C.c_int, [C.c_int, _PP, _PP, _PP, _PP, _I64P, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                     C.c_float, C.c_float, C.c_void_p]),
+    'coordx_interp_fuse': (C.c_int, [C.c_int, _PP, _I64P, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'coordx_infer_grid_host_workspace_bytes': (C.c_size_t, [C.POINTER(Net), _I64P, C.c_int]),
     'coordx_infer_grid_host': (C.c_int, [C.POINTER(Net), _PP, _I64P, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
                                          C.c_void_p]),

@@ -7,6 +7,7 @@
 #include "gemm_f32.cuh"
 #include "branch_fused.cuh"
 #include "sum_sep.cuh"
+#include "interp.cuh"
 #include "tc_common.cuh"
 
 namespace coordx {
@@ -562,6 +563,28 @@ int coordx_optim_step(int n_tensors, float* const* params, const float* const* g
   optim_adam_kernel<<<grid, 256, 0, st>>>(t, state, beta1, beta2, eps, max_grad_norm);
   CX_LAUNCH_CHECK();
   optim_advance_kernel<<<1, 1, 0, st>>>(state, lr_gamma);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+// -------------------------------------------------------------------------- feature-interpolated points
+int coordx_interp_fuse(int n_axes, const float* const* feats, const int64_t* n, int feat_width, int fusion_op,
+                       const float* idx, int64_t n_points, float* h, void* stream) {
+  if (n_axes < 1 || n_axes > COORDX_MAX_BRANCHES) return set_err(COORDX_ERR_ARG, "interp_fuse: bad axis count%s (%lld)", "", n_axes);
+  if (!feats || !n || !idx || !h) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (feat_width <= 0 || (feat_width & 3)) return set_err(COORDX_ERR_ARG, "interp_fuse: feature width must be a multiple of 4%s (%lld)", "", feat_width);
+  if (fusion_op != COORDX_FUSE_SUM && fusion_op != COORDX_FUSE_PROD) return set_err(COORDX_ERR_ARG, "unknown fusion operator%s (%lld)", "", fusion_op);
+  if (n_points <= 0) return 0;
+  InterpArgs a{};
+  a.C = n_axes; a.F = feat_width; a.op = fusion_op; a.idx = idx; a.P = n_points; a.h = h;
+  for (int c = 0; c < n_axes; ++c) {
+    if (!feats[c] || n[c] < 1) return set_err(COORDX_ERR_ARG, "interp_fuse: bad feature table%s (%lld)", "", c);
+    if (reinterpret_cast<uintptr_t>(feats[c]) & 15) return set_err(COORDX_ERR_ARG, "interp_fuse: feature table not 16-byte aligned%s (%lld)", "", c);
+    a.feat[c] = feats[c]; a.n[c] = n[c];
+  }
+  if (reinterpret_cast<uintptr_t>(h) & 15) return set_err(COORDX_ERR_ARG, "interp_fuse: output not 16-byte aligned%s");
+  const int64_t threads = n_points * (feat_width / 4);
+  interp_fuse_kernel<<<(unsigned)cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(a);
   CX_LAUNCH_CHECK();
   return 0;
 }

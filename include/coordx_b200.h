@@ -157,6 +157,13 @@ int coordx_optim_step(int n_tensors, float* const* params, const float* const* g
                       float* const* exp_avg_sq, const int64_t* numel, float* state, float beta1, float beta2,
                       float eps, float max_grad_norm, float lr_gamma, void* stream);
 
+/* ---- feature-interpolated points: the gather + lerp + fusion of ray_rendering.py:133-145 (get_pts_pred, split=True)
+ * idx [n_points, n_axes] fractional indices into feats[c] [n[c], feat_width]  ->  h [n_points, feat_width], the
+ * fused per-point features; they go through the trunk as a 1 x n_points grid (coordx_trunk_forward with a first
+ * table of one row holding the fusion's neutral element).                                                            */
+int coordx_interp_fuse(int n_axes, const float* const* feats, const int64_t* n, int feat_width, int fusion_op,
+                       const float* idx, int64_t n_points, float* h, void* stream);
+
 /* ---- whole-path inference with HOST buffers (the reference's --speed_test loop,
  * train_img.py:125-135): copies the per-axis coordinates in, runs branch + trunk, copies
  * the [P, out_width] result out.  Weights stay resident on the device (model.cuda()).    */

@@ -21,7 +21,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from coordx_b200 import modules as M, sharding                 # noqa: E402
 from coordx_b200 import loss_functions as LF                   # noqa: E402
-from coordx_b200.runtime import CapturedGrid                   # noqa: E402
+from coordx_b200.runtime import CapturedGrid, CapturedTrainStep   # noqa: E402
 
 SUSTAINED_TF = 1406.8
 
@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--no-graph', action='store_true')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -106,6 +107,13 @@ def main():
                 opt.step()
 
             tms = timed(step, max(args.steps // 2, 5), 3)
+            if not args.no_graph:
+                # the same iteration (incl. the NCCL all-reduce) replayed from one CUDA graph per rank
+                cap = CapturedTrainStep(model, coords, gt, loss='mse', lr=1e-4, world=world)
+                gms = timed(cap.replay, max(args.steps // 2, 5), 3)
+                rec.update(train_graph_ms=gms, train_graph_it_per_s=1e3 / gms,
+                           train_graph_frac_of_sustained_peak_all_gpus=3 * F / gms * 1e-9 / (SUSTAINED_TF * world))
+                del cap
             rec.update(train_ms=tms, train_it_per_s=1e3 / tms, train_frac_of_sustained_peak_all_gpus=3 * F / tms * 1e-9 / (SUSTAINED_TF * world),
                        train_note='eager iteration, one flat NCCL all-reduce of 198 657 gradient floats per step; slabs of 2160 rows are equal only when N divides 2160')
         if rank == 0:
