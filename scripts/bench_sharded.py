@@ -8,7 +8,7 @@
 
 Inference: CUDA-graph replay of the two-stage API on the rank's slab (no collective).  Training (4K image): the eager
 iteration model(dict) -> MSE -> backward -> ONE flat NCCL all-reduce of the weight gradients -> Adam.  Every number is
-CUDA-event time on the device, barrier + synchronize on both sides, MAX over ranks; rank 0 prints one JSON line per
+CUDA-event time on the device per step (median step), barrier + synchronize on both sides, MAX over ranks; rank 0 prints one JSON line per
 workload."""
 import argparse
 import json
@@ -58,7 +58,10 @@ def main():
             b.record()
             evs.append((a, b))
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        per = sorted(a.elapsed_time(b) for a, b in evs)
+        ms = per[len(per) // 2]                      # median step: the eager NCCL loop shows an occasional one-off ~180 ms stall
+        if per[-1] > 3 * ms and rank == 0:
+            print('# uneven steps (ms): ' + ' '.join(f'{v:.2f}' for v in per), file=sys.stderr, flush=True)
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
