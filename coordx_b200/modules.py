@@ -13,8 +13,8 @@ The scattered-point path `{'coords': ...}` (modules.py:257-309; SURVEY 8f "next"
 runs through the same kernels whenever no second derivative with respect to the
 coordinates can be asked for (`SplitFCBlock.scattered_impl`); with grad mode on and
 coordinates that require grad (summaries, diff_operators.gradient / laplace, the SDF
-loss) it stays the reference's torch-op sequence.  The un-split FCBlock baseline is
-plain torch ops.
+loss) it stays the reference's torch-op sequence.  The un-split FCBlock baseline takes the same kernels as a one-branch
+split net (`_FCAsSplit`) under the same rule.
 """
 from __future__ import annotations
 
@@ -323,8 +323,49 @@ class _FusionFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------- blocks
+class _FCAsSplit:
+    """An un-split FCBlock seen through the C ABI: a split net with ONE branch (`coord_linears[0]` = the first layer,
+    every hidden layer but the last = the branch's shared layers) whose "fusion" multiplies by a one-row table of
+    ones, followed by the trunk (last hidden layer + output layer).  Same arithmetic as `FCBlock.net(coords)`
+    (BatchLinear + activation per layer, modules.py:42-107); it lets the baseline the paper's speed-up is defined
+    against (train_img.py:115-123) run on the same kernels: per-layer 3xTF32 GEMMs over the P points, then the
+    tcgen05 trunk."""
+
+    def __init__(self, fc: 'FCBlock'):
+        lins = [seq[0] for seq in fc.net]
+        self.split_channels = 1
+        self.feat_per_channel = [lins[0].in_features]
+        self.first, self.layers = lins[0], lins[1:]
+        self.layer_dims = [(l.out_features, l.in_features) for l in self.layers]
+        self.approx_layers = max(len(self.layers) - 2, 0)           # all hidden layers but one are "pre-fusion"
+        self.pre_width = lins[0].out_features
+        self.fuse_width = self.layer_dims[self.approx_layers - 1][0] if self.approx_layers > 0 else self.pre_width
+        self.fusion_feat_size = self.fuse_width
+        self.out_width = self.layer_dims[-1][0]
+        self.nonlinearity = fc.nonlinearity
+        self.fusion_operator, self.fusion_before_act, self.learn_code, self.act_scale = 'prod', False, False, 1.0
+        self.precision = fc.precision
+
+    def abi_params(self):
+        ps = [self.first.weight, self.first.bias]
+        for l in self.layers:
+            ps += [l.weight, l.bias]
+        return ps
+
+    def branch_param_mask(self, branch):
+        return [True, True] + [k < self.approx_layers for k in range(len(self.layers)) for _ in (0, 1)]
+
+    def trunk_param_mask(self):
+        return [False, False] + [k >= self.approx_layers for k in range(len(self.layers)) for _ in (0, 1)]
+
+    def resolve_precision(self, net, precision=None):
+        return SplitFCBlock.resolve_precision(self, net, precision)
+
+
 class FCBlock(nn.Module):
-    """Un-split MLP baseline (modules.py:42-129) - plain torch ops, off the hot path."""
+    """Un-split MLP baseline (modules.py:42-129).  `fused_impl`: 'auto' (default) runs CUDA inputs through the split
+    path's kernels (see _FCAsSplit) unless gradients with respect to the coordinates may be asked for; 'eager' is the
+    reference's nn.Sequential."""
 
     def __init__(self, in_features, out_features, num_hidden_layers, hidden_features, outermost_linear=False,
                  nonlinearity='relu', weight_init=None, approx_layers=2, fusion_size=1, reduced=False):
@@ -347,8 +388,31 @@ class FCBlock(nn.Module):
         self.net.apply(self.weight_init)
         if first_init is not None:
             self.net[0].apply(first_init)
+        self.nonlinearity, self.precision, self.fused_impl = nonlinearity, None, 'auto'
+        # representable as a one-branch split net: sine / relu, linear output layer, at least one hidden layer after
+        # the first, no group-sum widths
+        self._fusable = (nonlinearity in ('sine', 'relu') and outermost_linear and num_hidden_layers >= 1 and
+                         fusion_size == 1 and not reduced)
 
     def forward(self, coords, params=None, **kwargs):
+        if self.fused_impl not in ('auto', 'eager'):
+            raise ValueError(f'unknown fused_impl {self.fused_impl!r}')
+        if (self.fused_impl == 'auto' and self._fusable and coords.is_cuda and coords.numel() > 0 and
+                not (torch.is_grad_enabled() and coords.requires_grad)):
+            v = self.__dict__.get('_split_view')
+            if v is None:
+                v = self.__dict__['_split_view'] = _FCAsSplit(self)
+            v.precision = self.precision
+            lead = coords.shape[:-1]
+            x = coords.reshape(-1, coords.shape[-1])
+            ps = v.abi_params()
+            h = _BranchFn.apply(v, 0, x, *ps) if _needs_grad([x, *ps]) else _branch_forward(v, 0, x, ps)[0]
+            neutral = torch.ones(1, h.shape[-1], dtype=h.dtype, device=h.device)
+            if _needs_grad([h, *ps]):
+                out = _FusionFn.apply(v, None, 2, neutral, h, *ps)
+            else:
+                out = _fusion_forward(v, None, [neutral, h], ps)[0]
+            return out.reshape(*lead, out.shape[-1])
         return self.net(coords)
 
 
@@ -754,6 +818,7 @@ class SingleBVPNet(nn.Module):
                                hidden_features=hidden_features, outermost_linear=True, nonlinearity=type,
                                approx_layers=kwargs.get('approx_layers', 2), fusion_size=kwargs.get('fusion_size', 1),
                                reduced=kwargs.get('reduced', False))
+            self.net.precision = precision
         else:
             self.net = SplitFCBlock(in_features=in_features, out_features=out_features,
                                     num_hidden_layers=num_hidden_layers, hidden_features=hidden_features,
