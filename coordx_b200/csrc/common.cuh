@@ -65,11 +65,52 @@ struct Arena {
 // otherwise inline dozens of copies (a 160 KB kernel spends 40 % of its stalls on instruction-cache misses)
 static __device__ __noinline__ float sin_accurate(float x) { return sinf(x); }
 static __device__ __noinline__ float cos_accurate(float x) { return cosf(x); }
+// Inlinable accurate sin / cos: the libdevice sinf / cosf carry their Payne-Hanek slow path (|x| > 105615, ~120
+// instructions and a local-memory array) into every inlined copy, which is what made unrolled epilogues too large.
+// Here only the fast path is inline - 3-term Cody-Waite reduction by pi/2 and the single-precision minimax
+// polynomials on [-pi/4, pi/4] (max error ~1.5 ulp, the same class as sinf) - and the rare huge argument takes the
+// out-of-line libdevice call.  25 instructions per value, independent chains interleave freely.
+__device__ __forceinline__ void sincos_reduce(float x, float& r, int& q) {
+  const float n = rintf(x * 0.63661977236758134f);
+  r = fmaf(n, -1.57079601287841796875f, x);            // pi/2 split into three parts (24 + 24 + rest bits)
+  r = fmaf(n, -3.1391647326017846353352069854736e-7f, r);
+  r = fmaf(n, -5.3903025299577648829435417064e-15f, r);
+  q = (int)n;
+}
+__device__ __forceinline__ float sin_poly(float r) {
+  const float r2 = r * r;
+  float p = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  p = fmaf(p, r2, -1.6666654611e-1f);
+  return fmaf(p * r2, r, r);
+}
+__device__ __forceinline__ float cos_poly(float r) {
+  const float r2 = r * r;
+  float p = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  p = fmaf(p, r2, 4.166664568298827e-2f);
+  return fmaf(p * r2, r2, fmaf(r2, -0.5f, 1.0f));
+}
+__device__ __forceinline__ float sin_inl(float x) {
+  if (fabsf(x) > 48000.f) return sin_accurate(x);
+  float r;
+  int q;
+  sincos_reduce(x, r, q);
+  const float v = (q & 1) ? cos_poly(r) : sin_poly(r);
+  return (q & 2) ? -v : v;
+}
+__device__ __forceinline__ float cos_inl(float x) {
+  if (fabsf(x) > 48000.f) return cos_accurate(x);
+  float r;
+  int q;
+  sincos_reduce(x, r, q);
+  const float v = (q & 1) ? sin_poly(r) : cos_poly(r);
+  return ((q + 1) & 2) ? -v : v;
+}
+
 __device__ __forceinline__ float act_fwd(int act, float S, float z) {
-  return act == COORDX_ACT_SINE ? sin_accurate(S * z) : fmaxf(z, 0.f);
+  return act == COORDX_ACT_SINE ? sin_inl(S * z) : fmaxf(z, 0.f);
 }
 __device__ __forceinline__ float act_grad(int act, float S, float z) {
-  return act == COORDX_ACT_SINE ? S * cos_accurate(S * z) : (z > 0.f ? 1.f : 0.f);
+  return act == COORDX_ACT_SINE ? S * cos_inl(S * z) : (z > 0.f ? 1.f : 0.f);
 }
 
 }  // namespace coordx

@@ -66,9 +66,9 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
-__device__ __forceinline__ float act_fwd_inl(int act, float S, float z) { return act == COORDX_ACT_SINE ? sinf(S * z) : fmaxf(z, 0.f); }
+__device__ __forceinline__ float act_fwd_inl(int act, float S, float z) { return act == COORDX_ACT_SINE ? sin_inl(S * z) : fmaxf(z, 0.f); }
 __device__ __forceinline__ float act_grad_inl(int act, float S, float z) {
-  return act == COORDX_ACT_SINE ? S * cosf(S * z) : (z > 0.f ? 1.f : 0.f);
+  return act == COORDX_ACT_SINE ? S * cos_inl(S * z) : (z > 0.f ? 1.f : 0.f);
 }
 
 __device__ __forceinline__ float rn_tf32(float v) {
