@@ -222,9 +222,31 @@ linear_narrow_kernel(const float* __restrict__ X, int64_t ldx, const float* __re
 }
 
 // Y = act(X W^T + b*bscale); Z (pre-activation) optional.  X [M,K] (ld ldx), W [N,K].
+// Tiny reduction (K <= 4: coord_linears on raw coordinates, f_c = 1..3): an elementwise kernel, one thread per output,
+// coalesced along n - a 64 x 64-tile GEMM spends its time on k-steps that are all zero padding.
+__global__ void __launch_bounds__(256)
+linear_smallk_kernel(const float* __restrict__ X, int64_t ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                     float bscale, int64_t M, int N, int K, float* __restrict__ Y, float* __restrict__ Z, int64_t ldc, int act, float S) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int64_t m = idx / N;
+  const int n = (int)(idx - m * N);
+  float v = bias ? __ldg(bias + n) * bscale : 0.f;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc = fmaf(__ldg(X + m * ldx + k), __ldg(W + (int64_t)n * K + k), acc);
+  v += acc;                                            // (x . w) + b: the reference's matmul-then-add order
+  if (Z) Z[m * ldc + n] = v;
+  if (Y) Y[m * ldc + n] = act < 0 ? v : act_fwd(act, S, v);
+}
+
 static int linear_forward(const float* X, int64_t ldx, const float* W, const float* bias, float bscale, int M, int N,
                           int K, float* Y, float* Z, int64_t ldc, int act, float S, cudaStream_t st) {
   if (M <= 0) return 0;
+  if (K <= 4 && N > 8) {
+    linear_smallk_kernel<<<(unsigned)cdiv((int64_t)M * N, 256), 256, 0, st>>>(X, ldx, W, bias, bscale, M, N, K, Y, Z, ldc, act, S);
+    CX_LAUNCH_CHECK();
+    return 0;
+  }
   if (N <= 8) {
     int blocks = (int)cdiv((int64_t)M * 32, 256);
     linear_narrow_kernel<8><<<blocks, 256, 0, st>>>(X, ldx, W, bias, bscale, M, N, K, Y, Z, ldc, act, S);
