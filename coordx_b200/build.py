@@ -1,10 +1,11 @@
 """Build libcoordx_b200.so (the C-ABI library of include/coordx_b200.h) in-tree with nvcc
 for sm_100a.  `python -m coordx_b200.build` or `__graft_entry__.build()`.
 
-Three translation units compiled in parallel and linked into one shared library:
+Four translation units compiled in parallel and linked into one shared library:
   coordx_abi.cu     C ABI + the FP32 (FFMA) kernels
   trunk_fwd_tc.cu   tcgen05 fused fusion+trunk forward (CTA pair)
-  trunk_bwd_tc.cu   tcgen05 fused trunk backward
+  trunk_bwd_tc.cu   tcgen05 fused trunk backward: host side, recompute (fallback) passes
+  trunk_bwd_tc2.cu  tcgen05 trunk backward: dW pass (W_h / dZ^T in tensor memory) and the merged feature-gradient pass
 """
 import os
 import subprocess
@@ -15,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, '_build')
 LIB = os.path.join(HERE, 'libcoordx_b200.so')
-UNITS = ['coordx_abi.cu', 'trunk_fwd_tc.cu', 'trunk_bwd_tc.cu']
+UNITS = ['coordx_abi.cu', 'trunk_fwd_tc.cu', 'trunk_bwd_tc.cu', 'trunk_bwd_tc2.cu']
 HEADERS = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cuh', '.h'))] + \
           [os.path.join(os.path.dirname(HERE), 'include', 'coordx_b200.h')]
 

@@ -31,23 +31,10 @@
 // 16-19 producers | 20 MMA issuer.
 #include <stdlib.h>
 
-#include "tc_common.cuh"
+#include "trunk_bwd_common.cuh"
 
 namespace coordx {
 namespace tcb {
-using namespace tc;
-
-constexpr uint32_t W_CHUNK_BYTES = HD * 128;        // 32 KB: [256 rows x 128 B]
-constexpr uint32_t W_BYTES = NKC * W_CHUNK_BYTES;   // 128 KB
-constexpr uint32_t A_CHUNK_BYTES = TILE_M * 128;    // 16 KB
-constexpr uint32_t INNER_BYTES = NKC * A_CHUNK_BYTES;  // 64 KB per 128-row block
-
-template <typename T>
-__device__ __forceinline__ T to_T(float v);
-template <>
-__device__ __forceinline__ __nv_bfloat16 to_T<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-template <>
-__device__ __forceinline__ __half to_T<__half>(float v) { return __float2half_rn(v); }
 
 // W fp32 [256(n), 256(k)] -> 4 K-chunks of [256 rows x 128 B] SWIZZLE_128B; epilogue constants
 template <typename T>
@@ -102,45 +89,6 @@ prep_rowvec16_kernel(const float* __restrict__ t0, const float* __restrict__ t1,
   reinterpret_cast<T*>(img)[idx] = to_T<T>(v);
 }
 
-constexpr uint32_t CH = 16384;                    // one [128 rows x 128 B] SWIZZLE_128B chunk
-constexpr uint32_t SM_W = 0;                      // 4 chunks (64 KB): this CTA's 128 output features of W
-// dH pass:  H 4 chunks | dZ^T 2 chunks | inner block 4 chunks          dW pass:  H stage 0 | H stage 1 | dZ^T 2 chunks
-constexpr uint32_t SM_H = 4 * CH;
-constexpr uint32_t SM_DZ_DH = 8 * CH, SM_INNER = 10 * CH;
-constexpr uint32_t SM_H1 = 8 * CH, SM_DZ_DW = 12 * CH;
-constexpr uint32_t SM_BAR = 14 * CH;
-constexpr uint32_t SM_DOUT = SM_BAR + 256;        // float dout[128 points][MAX_O] of the current tile (staged by the producers)
-constexpr uint32_t SM_TOTAL_B = SM_DOUT + TILE_M * MAX_O * 4;     // 231680 bytes <= 227 KB
-constexpr uint32_t SM_RV = SM_DOUT + 1024;        // O <= 2: two 512-byte rowvec slots in the unused tail of the dout staging area
-// dH pass: 0-7 E1 | 8-15 E2 | 16-19 producers | 20 MMA.   dW pass: 0-7 E1 | 8-15 producers | 16 MMA.
-constexpr int DH_THREADS = 21 * 32, DW_THREADS = 17 * 32;
-
-struct BwdParams {
-  const uint8_t* w_img;      // full W image of the forward prep: 4 K-chunks of [256 rows x 128 B]
-  const uint8_t* inner_img;  // inner axis table, per 128-row block 4 K-chunks [128 x 128 B]   (dH pass)
-  const float* inner_f32;    // the same table as fp32 [n_inner, 256]                           (dW pass)
-  const float* w_f32;        // trunk weight [256 n_out, 256 k_in] fp32                          (dH pass, E2)
-  long long* trace;          // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
-  const uint8_t* outer_img;  // optional: the outer0 table as 16-bit rows [n, 256] (512 B each): dH-pass producers fetch rowvec(o) with
-                             // the copy engine two tiles ahead instead of global loads on their critical path (outer1 == nullptr only)
-  float* d_inner;            // [n_inner, 256] +=  gradient w.r.t. the inner axis' features (din pass)
-  uint8_t* dz_img;           // optional: dZ^T_h tiles, 32 KB per (tile, h), written by the dW pass and read by the drv pass
-  const float* consts;       // [256] bias' then [MAX_O][256] wfs (see prep_bwd_consts_kernel)
-  const float* outer0;
-  const float* outer1;
-  int64_t n_outer1;
-  int64_t o_begin, o_end;
-  int64_t n_inner;
-  int nb;
-  const float* dout;         // element (o_local, j, oo) at (o_local*stride_o + j*stride_j)*O + oo
-  int64_t stride_o, stride_j;
-  float* d_rv;               // [n_o, 256] +=   (gradient w.r.t. rowvec(o))
-  float* dW;                 // [256, 256] +=   (DO_DW)
-  float* db;                 // [256] +=
-  float* dWf;                // [O, 256] +=
-  float S;
-};
-
 // sine: bias' = S b, wfs = S Wf  (dz = dout . wfs * cos(S z + bias'));  relu: bias' = b, wfs = Wf
 __global__ void __launch_bounds__(256)
 prep_bwd_consts_kernel(const float* __restrict__ b, const float* __restrict__ Wf, int O, int act, float S, float* __restrict__ consts) {
@@ -148,6 +96,40 @@ prep_bwd_consts_kernel(const float* __restrict__ b, const float* __restrict__ Wf
   const float sc = act == COORDX_ACT_SINE ? S : 1.f;
   if (i < HD) consts[i] = sc * b[i];
   if (i < MAX_O * HD) consts[HD + i] = (i >> 8) < O ? sc * Wf[i] : 0.f;
+}
+
+// max |x| over a tensor, as the bit pattern of a non-negative float (atomicMax on unsigned keeps the order)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// Power-of-two loss scale for 16-bit dZ (fp16 operands only; bf16 has fp32's exponent range and uses 1):
+// dZ = dout . wfs * act' is packed to fp16 before the gradient GEMMs; with mean losses dout ~ 2 e / P, which is below
+// fp16's normal range from ~512^2 points on.  The scale puts max|dout| * max|wfs| at 2^12; every accumulator that
+// holds scaled values is multiplied by the exact inverse when it is flushed.
+__global__ void __launch_bounds__(256)
+prep_scale_kernel(float* __restrict__ consts, int O, int enable) {
+  __shared__ float red[8];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < O * HD; i += 256) m = fmaxf(m, fabsf(consts[HD + i]));
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    const float maxd = __uint_as_float(reinterpret_cast<const unsigned*>(consts)[CONST_SCALE + 2]);
+    const float prod = maxd * m;
+    int e = 0;
+    if (enable && prod > 0.f && isfinite(prod)) e = min(max((int)floorf(log2f(4096.f / prod)), -60), 60);
+    consts[CONST_SCALE] = exp2f((float)e);
+    consts[CONST_SCALE + 1] = exp2f((float)-e);
+  }
 }
 
 // column sums over the 32 lanes of a warp: on return lane l holds sum over lanes of v[l]
@@ -188,11 +170,6 @@ __device__ __forceinline__ void unpack8<__half>(const uint4& q, float (&f)[8]) {
 }
 
 
-constexpr int TRACE_ITERS = 96;
-__device__ __forceinline__ void trace_stamp(const BwdParams& p, int role, int it, int slot) {
-  if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_ITERS) p.trace[(role * TRACE_ITERS + it) * 4 + slot] = clock64();
-}
-
 // barrier block (byte offsets from SM_BAR), shared by the two kernels
 struct Bars {
   uint32_t full, empty;      // [4] H chunk (dH pass) / [2] H stage (dW pass)
@@ -221,9 +198,10 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
   const int q = warp & 3, hh = warp >> 2;
   const int row = q * 32 + lane;
   const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
-  float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]
+  const float gscale = p.consts[CONST_SCALE], ginv = p.consts[CONST_SCALE + 1];   // power-of-two loss scale (fp16 operands)
+  float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]   (times the loss scale)
 #pragma unroll
-  for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row];
+  for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row] * gscale;
   float db_acc = 0.f;
   float dwf_acc[O];
 #pragma unroll
@@ -327,7 +305,7 @@ __device__ __forceinline__ void e1_stage(const BwdParams& p, const Bars& B, uint
     if (warp == 0 && lane == 0) trace_stamp(p, 1, t, 3);
   }
   if (DO_DW && my_tiles > 0) {
-    atomicAdd(p.db + h * 128 + row, db_acc);
+    atomicAdd(p.db + h * 128 + row, db_acc * ginv);
 #pragma unroll
     for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
   }
@@ -342,26 +320,6 @@ __device__ __forceinline__ float ld_el<__nv_bfloat16>(const uint8_t* p) {
 }
 template <>
 __device__ __forceinline__ float ld_el<__half>(const uint8_t* p) { return __half2float(*reinterpret_cast<const __half*>(p)); }
-
-// rowvec(o) piece: 8 fp32 values of outer0[i0] (+|*) outer1[i1] starting at column k0
-template <int OP>
-__device__ __forceinline__ void load_rowvec8(const BwdParams& p, int64_t o, int k0, float4& x0, float4& x1) {
-  int64_t i0 = o, i1 = 0;
-  if (p.outer1) { i0 = o / p.n_outer1; i1 = o - i0 * p.n_outer1; }
-  x0 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + k0);
-  x1 = *reinterpret_cast<const float4*>(p.outer0 + i0 * HD + k0 + 4);
-  if (p.outer1) {
-    const float4 y0 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + k0);
-    const float4 y1 = *reinterpret_cast<const float4*>(p.outer1 + i1 * HD + k0 + 4);
-    if (OP == COORDX_FUSE_PROD) {
-      x0.x *= y0.x; x0.y *= y0.y; x0.z *= y0.z; x0.w *= y0.w;
-      x1.x *= y1.x; x1.y *= y1.y; x1.z *= y1.z; x1.w *= y1.w;
-    } else {
-      x0.x += y0.x; x0.y += y0.y; x0.z += y0.z; x0.w += y0.w;
-      x1.x += y1.x; x1.y += y1.y; x1.z += y1.z; x1.w += y1.w;
-    }
-  }
-}
 
 // =================================================================================
 // dW pass:  G1 Z^T = W_h H^T  ->  E1 (sin + cos; db, dWf)  ->  G3 dW_h += dZ^T H     (dW, db, dWf)
@@ -561,6 +519,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
       ptx::mbar_wait(B.dwfull, 0);
       ptx::tc_fence_after();
       const int q = warp & 3, ch = warp >> 2;
+      const float ginv_flush = p.consts[CONST_SCALE + 1];
       float* drow = p.dW + (size_t)(h * 128 + q * 32 + lane) * HD + ch * 128;
 #pragma unroll 1
       for (int b = 0; b < 4; ++b) {
@@ -568,7 +527,7 @@ trunk_bwd_dw_kernel(const BwdParams p) {
         ptx::tmem_ld_32x32b_x32(tDW + ((uint32_t)(q * 32) << 16) + ch * 128 + b * 32, r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]) * ginv_flush);
       }
     }
   }
@@ -911,7 +870,7 @@ trunk_bwd_dh_kernel(const BwdParams p) {
           }
         }
       }
-      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, ((acc4[0] + acc4[1]) + (acc4[2] + acc4[3])) * p.consts[CONST_SCALE + 1]);
       if (OP == COORDX_FUSE_PROD) {
         __syncwarp();
         if (lane == 0) atomicAdd(const_cast<int*>(e2_done), 1);
@@ -1463,6 +1422,12 @@ static bool dz_reuse(int64_t tiles) {
   return (double)tiles * (4.0 * CH) <= max_gb * 1e9;
 }
 
+// COORDX_BWD_V1=1: the first-generation kernels (dW pass with W_h in shared memory, separate drv and din passes): A/B timing only
+static bool bwd_v1() {
+  const char* e = getenv("COORDX_BWD_V1");
+  return e && e[0] == '1';
+}
+
 static long long* g_bwd_trace = nullptr;
 static int g_bwd_trace_pass = 1;      // 0 = dW pass, 1 = dH pass A, 2 = dH pass B
 
@@ -1484,7 +1449,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   size_t off = 0;
   pl.w_img_off = off; off += align_up(W_BYTES, 1024);
   pl.epi_off = off;
-  pl.consts_off = off; off += align_up((1 + MAX_O) * HD * 4, 1024);
+  pl.consts_off = off; off += align_up(CONST_FLOATS * 4, 1024);
   pl.innerA_off = off; off += (size_t)pl.nbA * INNER_BYTES;
   pl.innerB_off = off; off += (size_t)pl.nbB * INNER_BYTES;
   pl.drv_off = off; off += C == 3 ? align_up((size_t)pl.n_oA * HD * 4, 1024) : 0;
@@ -1497,7 +1462,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
 
 template <typename T>
 static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
-                               const float* dout, coordx_grads* grads, float* const* dfeat, void* ws, size_t ws_bytes,
+                               const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws, size_t ws_bytes,
                                cudaStream_t st) {
   const int C = net->n_branches, L = net->n_pre, O = net->layer_out[L + 1];
   const BwdPlan pl = plan_bwd(net, n, r0, r1);
@@ -1516,6 +1481,17 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
                                                        O, net->act, S, w_img, nullptr);
   CX_LAUNCH_CHECK();
   prep_bwd_consts_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], O, net->act, S, consts);
+  CX_LAUNCH_CHECK();
+  const bool v1 = bwd_v1();
+  const bool fp16 = sizeof(T) == 2 && Pack<T>::kFmt == 0;
+  const int64_t n_pts = (r1 - r0) * n1 * n_last;
+  if (fp16 && !v1) {                               // max|dout| for the loss scale (bf16 needs none)
+    CX_CUDA(cudaMemsetAsync(consts + CONST_SCALE + 2, 0, 4, st));
+    absmax_kernel<<<(unsigned)min(cdiv(n_pts * O, 256 * 8), (int64_t)(4 * num_sms())), 256, 0, st>>>(dout, n_pts * O,
+                                                                                               (unsigned*)(consts + CONST_SCALE + 2));
+    CX_LAUNCH_CHECK();
+  }
+  prep_scale_kernel<<<1, 256, 0, st>>>(consts, O, fp16 && !v1 ? 1 : 0);
   CX_LAUNCH_CHECK();
   // ---------------- pass W: tiles = (outer index, 128 rows of the last axis): dW, db, dWf
   // ---------------- pass A: same tiles: d(outer features)
@@ -1539,12 +1515,25 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
     a.trace = g_bwd_trace_pass == 0 ? g_bwd_trace : nullptr;
     a.dz_img = pl.reuse ? base + pl.dz_off : nullptr;
-    CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
-    a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
-    if (pl.reuse)
-      CX_TRY((launch_drv<T>(a, net->fusion_op, grid, st)));
+    if (v1)
+      CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
     else
+      CX_TRY(launch_dw2(a, precision, net->fusion_op, net->act, O, grid, st));
+    a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
+    if (pl.reuse && !v1) {
+      // ---------------- dfeat pass: BOTH feature gradients from the stored dZ^T tiles, one GEMM per tile
+      prep_rowvec16_kernel<T><<<(unsigned)cdiv(pl.n_oA * HD, 256), 256, 0, st>>>(feats[0], C == 3 ? feats[1] : nullptr, r0, n1, pl.n_oA,
+                                                                                net->fusion_op, base + pl.rows_off);
+      CX_LAUNCH_CHECK();
+      a.outer_img = base + pl.rows_off;
+      a.d_inner = dfeat[C - 1];
+      a.trace = nullptr;
+      CX_TRY(launch_dfeat(a, precision, net->fusion_op, (int)min((int64_t)num_sms(), total), st));
+    } else if (pl.reuse) {
+      CX_TRY((launch_drv<T>(a, net->fusion_op, grid, st)));
+    } else {
       CX_TRY((launch_bwd_t<T, false>(a, net->fusion_op, net->act, O, grid, st)));
+    }
   }
   if (C == 3) {
     pair_scatter_kernel<<<(unsigned)cdiv((r1 - r0) * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 0, dfeat[0]);
@@ -1552,6 +1541,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     pair_scatter_kernel<<<(unsigned)cdiv(n1 * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 1, dfeat[1]);
     CX_LAUNCH_CHECK();
   }
+  if (pl.reuse && !v1) return 0;
   if (pl.reuse) {
     // ---------------- din pass: gradient of the last axis' features from the stored dZ^T tiles (same tiling)
     prep_rowvec16_kernel<T><<<(unsigned)cdiv(pl.n_oA * HD, 256), 256, 0, st>>>(feats[0], C == 3 ? feats[1] : nullptr, r0, n1, pl.n_oA,
@@ -1600,8 +1590,8 @@ int trunk_backward_tc(const coordx_net* net, const float* const* feats, const in
                       const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   if (precision == COORDX_PREC_BF16)
-    return tcb::trunk_backward_tc_t<__nv_bfloat16>(net, feats, n, r0, r1, dout, grads, dfeat, ws, ws_bytes, st);
-  return tcb::trunk_backward_tc_t<__half>(net, feats, n, r0, r1, dout, grads, dfeat, ws, ws_bytes, st);
+    return tcb::trunk_backward_tc_t<__nv_bfloat16>(net, feats, n, r0, r1, dout, grads, dfeat, precision, ws, ws_bytes, st);
+  return tcb::trunk_backward_tc_t<__half>(net, feats, n, r0, r1, dout, grads, dfeat, precision, ws, ws_bytes, st);
 }
 }  // namespace tc
 }  // namespace coordx

@@ -1,0 +1,682 @@
+// tcgen05 / TMEM trunk backward, second translation unit: the two kernels of the stored-dZ path
+// (what autograd does for SplitFCBlock.forward_fusion, modules.py:329-354, in training.py:137-138).
+//
+//   trunk_bwd_dw2_kernel    G1 Z^T = W_h H^T -> E1 (sin + cos; db, dWf) -> G3 dW_h += dZ^T H, dZ^T tiles -> HBM
+//   trunk_bwd_dfeat_kernel  dH^T = W^T dZ^T from the stored tiles, ONE GEMM per tile serving BOTH feature gradients:
+//                           d rowvec(o)[k] = sum_p dH[p,k] inner[p,k]   and   d inner[j,k] += rowvec(o)[k] dH[(o,j),k]
+//
+// dw2 differs from the first dW kernel (trunk_bwd_tc.cu) in where the operands live.  There, W_h (64 KB) sat in shared
+// memory next to two 64 KB H stages, and the chain  G3(t-1) -> H stage free -> producers -> G1(t+1) -> E1(t+1)  left
+// E1 - the longest stage, sin AND cos of every element - idle ~45 % of the time (profiles/r01e_bwd_dw_full.txt:
+// XU 46 %, tensor 44 %).  Here W_h is a TMEM-resident A operand (128 columns, written once), the Z^T double buffer
+// works on 64-point sub-tiles (2 x 64 columns), dZ^T is written back over the consumed Z^T columns as before, and the
+// 64 KB of shared memory that W_h occupied is a THIRD H stage: H(t+1) can be produced while G3(t-1) is still pending.
+// The bulk store of the dZ^T image moved from the MMA-issuing thread to a warp of its own.
+//
+// dfeat replaces the drv and din kernels: both streamed the same 2.1 GB (2048^2) of dZ^T tiles and each ran its own
+// GEMM.  With the output feature k on the TMEM lane, thread k owns dH^T[k, p]: the reduction over the points of a tile
+// (d rowvec) is a per-thread dot product with its column of the inner block, and the reduction over the outer index
+// (d inner) is a per-thread accumulator per point that lives in registers while the CTA sweeps o for a fixed block
+// of inner rows.  W^T is a TMEM-resident A operand (256 columns), so the tensor core fetches only the streamed dZ^T
+// tile from shared memory.
+#include "trunk_bwd_common.cuh"
+
+namespace coordx {
+namespace tcb {
+
+// =================================================================================
+// dW pass, second version
+// =================================================================================
+constexpr int D2_STAGES = 3;
+constexpr uint32_t D2_H = 0;                               // 3 stages x 4 chunks [128 points x 128 B]
+constexpr uint32_t D2_IMG = D2_STAGES * 4 * CH;            // 2 x 16 KB: dZ^T image of a 64-point sub-tile
+constexpr uint32_t D2_BAR = D2_IMG + 2 * CH;
+constexpr uint32_t D2_DOUT = D2_BAR + 256;                 // dout staging: D stages x 128 points x O floats
+constexpr int DW2_THREADS = 18 * 32;                       // 0-7 E1 | 8-15 producers | 16 MMA | 17 image store
+__host__ __device__ constexpr int d2_dout_stages(int O) { return O <= 2 ? 2 : 1; }
+__host__ __device__ constexpr uint32_t d2_smem_bytes(int O) { return D2_DOUT + d2_dout_stages(O) * TILE_M * O * 4; }
+
+struct Bars2 {
+  uint32_t full, empty;        // [3] H stage
+  uint32_t zfull;              // [2] Z^T sub-tile buffer (G1 commit)
+  uint32_t dzfull;             // [2] dZ^T written by E1 (256 threads): TMEM operand + image chunk
+  uint32_t imgempty;           // [2] the bulk store has read the image chunk
+  uint32_t dsfull, dsempty;    // [2] dout staging
+  uint32_t wfull, dwfull, tmem_slot;
+  __device__ explicit Bars2(uint32_t b0)
+      : full(b0), empty(b0 + 24), zfull(b0 + 48), dzfull(b0 + 64), imgempty(b0 + 80), dsfull(b0 + 96), dsempty(b0 + 112),
+        wfull(b0 + 128), dwfull(b0 + 136), tmem_slot(b0 + 144) {}
+};
+
+template <typename T, int OP, int ACT, int O>
+__global__ void __launch_bounds__(DW2_THREADS, 1)
+trunk_bwd_dw2_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Bars2 B(smem_base + D2_BAR);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + D2_BAR + 144);
+  constexpr int W_PROD = 8, W_MMA = 16, W_STORE = 17;
+  constexpr int DST = d2_dout_stages(O);
+
+  const int h = blockIdx.x & 1;                    // half of the trunk's output features
+  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int64_t t_begin = total * cta / n_cta;
+  const int64_t t_end = total * (cta + 1) / n_cta;
+  const int my_tiles = (int)(t_end - t_begin);
+  const int n_sub = 2 * my_tiles;
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int c = 0; c < D2_STAGES; ++c) {
+        ptx::mbar_init(B.full + 8 * c, 8);         // 8 producer warps
+        ptx::mbar_init(B.empty + 8 * c, 1);
+      }
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(B.zfull + 8 * c, 1);
+        ptx::mbar_init(B.dzfull + 8 * c, 256);
+        ptx::mbar_init(B.imgempty + 8 * c, 1);
+        ptx::mbar_init(B.dsfull + 8 * c, 128);
+        ptx::mbar_init(B.dsempty + 8 * c, 256);
+      }
+      ptx::mbar_init(B.wfull, 256);
+      ptx::mbar_init(B.dwfull, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(B.tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint32_t tZ = tmem_base, tW = tmem_base + 128, tDW = tmem_base + 256;
+
+  if (warp == W_MMA) {
+    // ============================ MMA issuer ============================
+    if (my_tiles > 0 && ptx::elect_one()) {       // (elect, not lane == 0: see ptx::elect_one)
+      constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 0, 0);    // A = W_h (TMEM, M = n_out), B = H (N = 64 points) K-major
+      constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (TMEM, M = n_out), B = H (N = k_in) MN-major
+      ptx::mbar_wait(B.wfull, 0);
+      ptx::tc_fence_after();
+      int st1 = 0, use1 = 0;                       // H stage / use count of the tile G1 works on
+      int st3 = 0;                                 // ... of the tile G3 works on
+      auto issue_g1 = [&](int s) {
+        const uint32_t zb = s & 1, hh = s & 1;
+        if (hh == 0) {
+          ptx::mbar_wait(B.full + 8 * st1, use1 & 1);
+          ptx::tc_fence_after();
+        }
+        // (no wait for the Z^T buffer: its last reader G3(s-2) is earlier in this thread's in-order tensor pipe)
+        const uint32_t hs = smem_base + D2_H + st1 * 4 * CH + hh * 8192;     // rows 64 hh .. 64 hh + 63 of every chunk
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          ptx::mma_f16_ts(tZ + zb * 64, tW + k * 8, ptx::umma_desc_k_sw128(hs + (k >> 2) * CH + (k & 3) * 32), id_g1, k != 0);
+        ptx::mma_commit(B.zfull + 8 * zb);
+        if (hh == 1 && ++st1 == D2_STAGES) { st1 = 0; ++use1; }
+      };
+      auto issue_g3 = [&](int s) {
+        const uint32_t zb = s & 1, hh = s & 1;
+        ptx::mbar_wait(B.dzfull + 8 * zb, (s >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t hs = smem_base + D2_H + st3 * 4 * CH;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)                // K = 64 points, 16 per step; the two E1 warps of a lane quadrant own 32 columns each
+          ptx::mma_f16_ts(tDW, tZ + zb * 64 + (j >> 1) * 32 + (j & 1) * 8, ptx::umma_desc_mn_sw128(hs + (hh * 4 + j) * 2048, CH), id_g3,
+                          (s | j) != 0);
+        if (hh == 1) {
+          ptx::mma_commit(B.empty + 8 * st3);      // H stage free for the producers
+          if (++st3 == D2_STAGES) st3 = 0;
+        }
+      };
+      // G1(s+1) is issued AHEAD of G3(s): E1 is the longest stage, its input must never queue behind G3
+      issue_g1(0);
+      for (int s = 0; s < n_sub; ++s) {
+        if (s + 1 < n_sub) issue_g1(s + 1);
+        issue_g3(s);
+      }
+      ptx::mma_commit(B.dwfull);
+    }
+    __syncwarp();
+  } else if (warp == W_STORE) {
+    // ============================ dZ^T image -> HBM (one 16 KB bulk store per sub-tile) ============================
+    if (p.dz_img != nullptr && my_tiles > 0 && ptx::elect_one()) {
+      for (int s = 0; s < n_sub; ++s) {
+        const int t = s >> 1, hh = s & 1;
+        ptx::mbar_wait(B.dzfull + 8 * (s & 1), (s >> 1) & 1);
+        ptx::bulk_s2g(p.dz_img + (((size_t)(t_begin + t) * 2 + h) * 2 + hh) * CH, smem_base + D2_IMG + (s & 1) * CH, CH);
+        ptx::bulk_commit_group();
+        if (s >= 1) {
+          ptx::bulk_wait_group_read<1>();          // the store of sub-tile s-1 has read its chunk
+          ptx::mbar_arrive(B.imgempty + 8 * ((s - 1) & 1));
+        }
+      }
+      ptx::bulk_wait_group0();
+    }
+    __syncwarp();
+  } else if (warp >= W_PROD) {
+    // ============================ producers: H tile (inner block piece in registers) ============================
+    // thread (g = lane, rg = warp - 8) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows 16 rg .. 16 rg + 15
+    const int g = lane, rg = warp - W_PROD;
+    const int ptid = threadIdx.x - W_PROD * 32;    // 0..255; the first 128 also stage dout
+    uint32_t in[16][4];
+    int64_t cur_jb = -1;
+    int st = 0, use = 0, dsg = 0, dsuse = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int64_t tt = t_begin + t;
+      const int64_t jb = tt / n_o;
+      const int64_t o_local = tt - jb * n_o;
+      uint32_t rv[4];
+      {
+        float4 x0, x1;
+        load_rowvec8<OP>(p, p.o_begin + o_local, 8 * g, x0, x1);      // L1 hit: prefetched during the previous tile
+        rv[0] = Pack<T>::pack(x0.x, x0.y);
+        rv[1] = Pack<T>::pack(x0.z, x0.w);
+        rv[2] = Pack<T>::pack(x1.x, x1.y);
+        rv[3] = Pack<T>::pack(x1.z, x1.w);
+      }
+      if (t + 1 < my_tiles) {                      // next tile's rowvec -> L1 while this tile is produced (no registers held)
+        const int64_t tn = tt + 1, jn = tn / n_o;
+        const int64_t on = p.o_begin + (tn - jn * n_o);
+        const int64_t i0 = p.outer1 ? on / p.n_outer1 : on;
+        ptx::prefetch_l1(p.outer0 + i0 * HD + 8 * g);
+        if (p.outer1) ptx::prefetch_l1(p.outer1 + (on - i0 * p.n_outer1) * HD + 8 * g);
+      }
+      float dreg[O];
+#pragma unroll
+      for (int oo = 0; oo < O; ++oo) dreg[oo] = 0.f;
+      if (ptid < TILE_M) {
+        const int64_t j = jb * TILE_M + ptid;
+        if (j < p.n_inner) {
+#pragma unroll
+          for (int oo = 0; oo < O; ++oo) dreg[oo] = __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo);
+        }
+      }
+      if (jb != cur_jb) {
+        uint32_t chain = 0;                        // batches of 4 rows chained through an opaque zero: bounds the loads in flight
+#pragma unroll
+        for (int r4 = 0; r4 < 16; r4 += 4) {
+          float4 v0[4], v1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t j = jb * TILE_M + rg * 16 + r4 + u;
+            v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            v1[u] = v0[u];
+            if (j < p.n_inner) {
+              const float* src = p.inner_f32 + j * HD + 8 * g + chain;
+              v0[u] = *reinterpret_cast<const float4*>(src);
+              v1[u] = *reinterpret_cast<const float4*>(src + 4);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            in[r4 + u][0] = Pack<T>::pack(v0[u].x, v0[u].y);
+            in[r4 + u][1] = Pack<T>::pack(v0[u].z, v0[u].w);
+            in[r4 + u][2] = Pack<T>::pack(v1[u].x, v1[u].y);
+            in[r4 + u][3] = Pack<T>::pack(v1[u].z, v1[u].w);
+          }
+          asm volatile("and.b32 %0, %1, 0;" : "=r"(chain) : "r"(in[r4 + 3][3]));
+        }
+        cur_jb = jb;
+      }
+      ptx::mbar_wait(B.empty + 8 * st, (use & 1) ^ 1);
+      uint8_t* dst = smem_gen + D2_H + (uint32_t)st * 4 * CH + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        uint4 w;
+        w.x = fuse2<T, OP>(in[r][0], rv[0]);
+        w.y = fuse2<T, OP>(in[r][1], rv[1]);
+        w.z = fuse2<T, OP>(in[r][2], rv[2]);
+        w.w = fuse2<T, OP>(in[r][3], rv[3]);
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(B.full + 8 * st);
+      if (++st == D2_STAGES) { st = 0; ++use; }
+      if (ptid < TILE_M) {
+        ptx::mbar_wait(B.dsempty + 8 * dsg, (dsuse & 1) ^ 1);    // E1 has read the dout that lived in this slot
+        float* ds = reinterpret_cast<float*>(smem_gen + D2_DOUT) + (dsg * TILE_M + ptid) * O;
+#pragma unroll
+        for (int oo = 0; oo < O; ++oo) ds[oo] = dreg[oo];
+        ptx::mbar_arrive(B.dsfull + 8 * dsg);
+      }
+      if (++dsg == DST) { dsg = 0; ++dsuse; }
+    }
+  } else {
+    // ============================ E1 (8 warps): Z^T sub-tile -> dZ^T (TMEM operand of G3 + image chunk) ============================
+    // thread = output feature n = 128 h + row; warp (q, pq) covers the 32 points [32 pq, 32 pq + 32) of the 64-point sub-tile.
+    // bias'[n], wfs[o][n] are registers; db[n] and dWf[o][n] are per-thread running sums (no cross-lane reduction).
+    const int q = warp & 3, pq = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    {
+      // W_h row n (this thread's TMEM lane), k in [128 pq, 128 pq + 128): the K-major A operand of G1, 16-bit pairs
+      const float* wrow = p.w_f32 + (size_t)(h * 128 + row) * HD + pq * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pkw[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(wrow + c * 32 + i * 4));
+          pkw[2 * i] = Pack<T>::pack(v.x, v.y);
+          pkw[2 * i + 1] = Pack<T>::pack(v.z, v.w);
+        }
+        ptx::tmem_st_32x32b_x16(tW + lane_base + pq * 64 + c * 16, pkw);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(B.wfull);
+    }
+    const float gscale = p.consts[CONST_SCALE], ginv = p.consts[CONST_SCALE + 1];   // power-of-two loss scale (fp16 operands)
+    const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
+    float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]   (times the loss scale)
+#pragma unroll
+    for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row] * gscale;
+    float db_acc = 0.f;
+    float dwf_acc[O];
+#pragma unroll
+    for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = 0.f;
+    int dsg = 0, dsuse = 0;
+    for (int s = 0; s < n_sub; ++s) {
+      const int hh = s & 1;
+      const uint32_t zb = s & 1;
+      if (warp == 0 && lane == 0) trace_stamp(p, 1, s, 0);
+      if (hh == 0) ptx::mbar_wait(B.dsfull + 8 * dsg, dsuse & 1);
+      ptx::mbar_wait(B.zfull + 8 * zb, (s >> 1) & 1);
+      if (warp == 0 && lane == 0) trace_stamp(p, 1, s, 1);
+      ptx::tc_fence_after();
+      const float* ds = reinterpret_cast<const float*>(smem_gen + D2_DOUT) + (dsg * TILE_M + hh * 64 + pq * 32) * O;
+      const uint32_t zaddr = tZ + zb * 64 + pq * 32 + lane_base;
+      uint32_t pk[16];
+      uint32_t ra[16], rb[16];
+      ptx::tmem_ld_32x32b_x16(zaddr, ra);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {                // 16 columns (points) per TMEM load, the second in flight during the first's arithmetic
+        uint32_t(&r)[16] = b ? rb : ra;
+        ptx::tmem_ld_wait();
+        if (b == 0) ptx::tmem_ld_32x32b_x16(zaddr + 16, rb);
+        float4 d4[4];                              // O == 1: dout of the batch's 16 points, 4 broadcast LDS.128
+        if (O == 1) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) d4[v] = *reinterpret_cast<const float4*>(ds + b * 16 + v * 4);
+        }
+#pragma unroll
+        for (int e2 = 0; e2 < 8; ++e2) {
+          float dz2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = e2 * 2 + u;
+            const float* dp = ds + (b * 16 + i) * O;              // warp-uniform shared-memory address: broadcast
+            float gw, d0 = 0.f;
+            if (O == 1) {
+              const float4 dv = d4[i >> 2];
+              d0 = (i & 3) == 0 ? dv.x : ((i & 3) == 1 ? dv.y : ((i & 3) == 2 ? dv.z : dv.w));
+              gw = d0 * wfs_n[0];
+            } else {
+              gw = 0.f;
+#pragma unroll
+              for (int oo = 0; oo < O; ++oo) gw = fmaf(dp[oo], wfs_n[oo], gw);
+            }
+            const float z = __uint_as_float(r[i]);
+            float av;                              // activation value (for dWf); the derivative is folded into dz
+            if (ACT == COORDX_ACT_SINE) {
+              const float th = fmaf(z, p.S, bias_n);
+              dz2[u] = gw * __cosf(th);
+              av = __sinf(th);
+            } else {
+              const float pre = z + bias_n;
+              dz2[u] = pre > 0.f ? gw : 0.f;
+              av = fmaxf(pre, 0.f);
+            }
+            db_acc += dz2[u];
+            if (O == 1) {
+              dwf_acc[0] = fmaf(d0, av, dwf_acc[0]);
+            } else {
+#pragma unroll
+              for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
+            }
+          }
+          pk[b * 8 + e2] = Pack<T>::pack(dz2[0], dz2[1]);
+        }
+      }
+      if (hh == 1) {
+        ptx::mbar_arrive(B.dsempty + 8 * dsg);     // last read of this tile's staged dout
+        if (++dsg == DST) { dsg = 0; ++dsuse; }
+      }
+      // dZ^T goes back into TENSOR MEMORY, over the first 16 of this warp's own 32 Z^T columns (all of them are in
+      // registers by now), as the A operand of G3.  No extra barrier: G1(s+2), the next writer of this buffer, is
+      // issued after G3(s) in the in-order tensor pipe.
+      ptx::tmem_st_32x32b_x16(zaddr, pk);
+      if (p.dz_img) {                              // the image for the dfeat pass: shared memory, then one bulk store per sub-tile
+        ptx::mbar_wait(B.imgempty + 8 * zb, ((s >> 1) & 1) ^ 1);
+        uint8_t* dzrow = smem_gen + D2_IMG + zb * CH;
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc)             // 8 points = one swizzled 16-byte piece of row n
+          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, (pq * 4 + pc) * 8)) =
+              make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+        ptx::fence_proxy_async();
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(B.dzfull + 8 * zb);
+      if (warp == 0 && lane == 0) trace_stamp(p, 1, s, 3);
+    }
+    if (my_tiles > 0) {
+      atomicAdd(p.db + h * 128 + row, db_acc * ginv);
+#pragma unroll
+      for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
+      // ---- flush dW_h (accumulated over every tile of this CTA) with one atomic per element
+      ptx::mbar_wait(B.dwfull, 0);
+      ptx::tc_fence_after();
+      float* drow = p.dW + (size_t)(h * 128 + row) * HD + pq * 128;
+#pragma unroll 1
+      for (int b = 0; b < 4; ++b) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tDW + lane_base + pq * 128 + b * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]) * ginv);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================
+// merged feature-gradient pass from the STORED dZ^T tiles
+// =================================================================================
+constexpr int DF_STAGES = 5;                               // ring of 64-point sub-tiles: 2 x 16 KB each (both halves of n)
+constexpr uint32_t DF_DZ = 0;
+constexpr uint32_t DF_INNER = DF_DZ + DF_STAGES * 2 * CH;  // 64 KB: per-thread column slice of the inner block (prod)
+constexpr uint32_t DF_BAR = DF_INNER + 4 * CH;
+constexpr uint32_t DF_TOTAL = DF_BAR + 256;
+constexpr int DF_THREADS = 18 * 32;                        // 0-15 E2 (group = warp >> 3 owns sub-tile hh = group) | 16 loader | 17 MMA
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(DF_THREADS, 1)
+trunk_bwd_dfeat_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_base + DF_BAR;
+  const uint32_t b_dzfull = bar0, b_dzempty = bar0 + 8 * DF_STAGES, b_accfull = bar0 + 16 * DF_STAGES, b_accempty = b_accfull + 16,
+                 b_wfull = b_accfull + 32, b_slot = b_accfull + 40;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + DF_BAR + 16 * DF_STAGES + 40);
+  constexpr int W_LOAD = 16, W_MMA = 17;
+
+  const int n_cta = gridDim.x, cta = blockIdx.x;
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int64_t t_begin = total * cta / n_cta;
+  const int64_t t_end = total * (cta + 1) / n_cta;
+  const int my_tiles = (int)(t_end - t_begin);
+  const int n_sub = 2 * my_tiles;
+  const int n_o32 = (int)n_o;
+  const int64_t jb0 = my_tiles > 0 ? t_begin / n_o : 0;
+  const int o0 = my_tiles > 0 ? (int)(t_begin - jb0 * n_o) : 0;
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < DF_STAGES; ++s) {
+        ptx::mbar_init(b_dzfull + 8 * s, 1);
+        ptx::mbar_init(b_dzempty + 8 * s, 1);
+      }
+      for (int c = 0; c < 2; ++c) {
+        ptx::mbar_init(b_accfull + 8 * c, 1);
+        ptx::mbar_init(b_accempty + 8 * c, 256);
+      }
+      ptx::mbar_init(b_wfull, 512);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(b_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint32_t tA = tmem_base, tAcc = tmem_base + 256;
+
+  if (warp == W_LOAD) {
+    // ============================ loader: ring of dZ^T sub-tiles (h = 0 and h = 1 chunks) ============================
+    if (my_tiles > 0 && ptx::elect_one()) {
+      int stg = 0, use = 0;
+      for (int s = 0; s < n_sub; ++s) {
+        const int t = s >> 1, hh = s & 1;
+        ptx::mbar_wait(b_dzempty + 8 * stg, (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(b_dzfull + 8 * stg, 2 * CH);
+        const uint8_t* src = p.dz_img + ((size_t)(t_begin + t) * 4 + hh) * CH;
+        ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH, src, CH, b_dzfull + 8 * stg);               // h = 0
+        ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH + CH, src + 2 * CH, CH, b_dzfull + 8 * stg);  // h = 1
+        if (++stg == DF_STAGES) { stg = 0; ++use; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_MMA) {
+    // ============================ MMA issuer: dH^T[k, p] = sum_n W^T[k, n] dZ^T[n, p] ============================
+    if (my_tiles > 0 && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 0, 1);   // A in tensor memory, B = dZ^T (N = 64 points) MN-major
+      ptx::mbar_wait(b_wfull, 0);
+      ptx::tc_fence_after();
+      int stg = 0, use = 0;
+      for (int s = 0; s < n_sub; ++s) {
+        const int hh = s & 1;
+        ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
+        ptx::mbar_wait(b_accempty + 8 * hh, ((s >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t dz = smem_base + DF_DZ + stg * 2 * CH;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)          // K = 256 output features n: 8 steps in the h = 0 chunk, 8 in the h = 1 chunk
+            ptx::mma_f16_ts(tAcc + hh * 128 + blk * 64, tA + blk * 128 + ks * 8,
+                            ptx::umma_desc_mn_sw128(dz + (ks >> 3) * CH + (ks & 7) * 2048, CH), idesc, ks != 0);
+        }
+        ptx::mma_commit(b_accfull + 8 * hh);
+        ptx::mma_commit(b_dzempty + 8 * stg);
+        if (++stg == DF_STAGES) { stg = 0; ++use; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ E2: dH^T sub-tile -> d rowvec(o) (atomics per tile) and d inner (registers) ============================
+    const int g = warp >> 3, q = warp & 3, blk = (warp >> 2) & 1;
+    const int k = blk * 128 + q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    {
+      // W^T: lane k, n in [128 g, 128 g + 128) as 16-bit pairs: columns 64 g .. 64 g + 63 of this M-block's A operand
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pkw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = g * 128 + c * 32 + 2 * i;
+          pkw[i] = Pack<T>::pack(__ldg(p.w_f32 + (size_t)n * HD + k), __ldg(p.w_f32 + (size_t)(n + 1) * HD + k));
+        }
+        ptx::tmem_st_32x32b_x16(tA + lane_base + blk * 128 + g * 64 + c * 16, pkw);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(b_wfull);
+    }
+    const float ginv = p.consts[CONST_SCALE + 1];
+    uint4* my_inner = reinterpret_cast<uint4*>(smem_gen + DF_INNER) + threadIdx.x;     // slot i at [i * 512 + thread]: conflict-free
+    float din[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) din[i] = 0.f;
+    auto load_inner = [&](int64_t jb) {            // this thread's column k of the 64 inner rows of its sub-tile, 16-bit
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t j = jb * TILE_M + g * 64 + c * 8 + i;
+          v[i] = j < p.n_inner ? __ldg(p.inner_f32 + j * HD + k) : 0.f;
+        }
+        my_inner[c * 512] = make_uint4(Pack<T>::pack(v[0], v[1]), Pack<T>::pack(v[2], v[3]), Pack<T>::pack(v[4], v[5]),
+                                       Pack<T>::pack(v[6], v[7]));
+      }
+    };
+    auto flush_din = [&](int64_t jb) {
+      float* dcol = p.d_inner + (jb * TILE_M + g * 64) * HD + k;        // lanes = consecutive k: coalesced atomics
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        if (jb * TILE_M + g * 64 + i < p.n_inner) atomicAdd(dcol + (size_t)i * HD, din[i] * ginv);
+        din[i] = 0.f;
+      }
+    };
+    auto load_rv = [&](int o_local) -> float {     // rowvec(o)[k] as the 16-bit value the forward multiplied with
+      if (OP != COORDX_FUSE_PROD) return 1.f;
+      const uint32_t e = __ldg(reinterpret_cast<const uint16_t*>(p.outer_img) + (size_t)o_local * HD + k);
+      return Pack<T>::unpack(e, 0);
+    };
+    int64_t jb = jb0;
+    int o_local = o0;
+    if (OP == COORDX_FUSE_PROD && my_tiles > 0) load_inner(jb);
+    float rv_next = my_tiles > 0 ? load_rv(o_local) : 0.f;
+    for (int t = 0; t < my_tiles; ++t) {
+      const float rv = rv_next;
+      {
+        int on = o_local + 1;
+        if (on == n_o32) on = 0;
+        if (t + 1 < my_tiles) rv_next = load_rv(on);                   // in flight during this tile
+      }
+      ptx::mbar_wait(b_accfull + 8 * g, t & 1);
+      ptx::tc_fence_after();
+      float acc2[2] = {0.f, 0.f};
+      const uint32_t tacc = tAcc + g * 128 + blk * 64 + lane_base;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(tacc + b * 16, r);
+        uint4 iv[2];
+        if (OP == COORDX_FUSE_PROD) {
+          iv[0] = my_inner[(2 * b) * 512];
+          iv[1] = my_inner[(2 * b + 1) * 512];
+        }
+        ptx::tmem_ld_wait();
+        if (b == 3) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(b_accempty + 8 * g);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float dh = __uint_as_float(r[i]);
+          if (OP == COORDX_FUSE_PROD) {
+            const uint4 v = iv[i >> 3];
+            const uint32_t w = ((i >> 1) & 3) == 0 ? v.x : (((i >> 1) & 3) == 1 ? v.y : (((i >> 1) & 3) == 2 ? v.z : v.w));
+            acc2[i & 1] = fmaf(dh, Pack<T>::unpack(w, i & 1), acc2[i & 1]);
+            din[b * 16 + i] = fmaf(rv, dh, din[b * 16 + i]);
+          } else {
+            acc2[i & 1] += dh;
+            din[b * 16 + i] += dh;
+          }
+        }
+      }
+      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (acc2[0] + acc2[1]) * ginv);
+      if (++o_local == n_o32) {                    // the sweep over the outer index is complete for this block of inner rows
+        o_local = 0;
+        flush_din(jb);
+        ++jb;
+        if (OP == COORDX_FUSE_PROD && t + 1 < my_tiles) load_inner(jb);
+      }
+    }
+    if (my_tiles > 0 && o_local != 0) flush_din(jb);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+// cudaFuncSetAttribute is per DEVICE: one flag per (kernel instantiation, device ordinal)
+struct AttrOnce {
+  bool done[64] = {};
+  template <typename K>
+  int set(K kern, int bytes) {
+    int dev = 0;
+    CX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return 0;
+  }
+};
+
+template <typename T, int OP, int ACT, int O>
+static int launch_dw2_inst(const BwdParams& bp, int grid, cudaStream_t st) {
+  static AttrOnce once;
+  auto kern = trunk_bwd_dw2_kernel<T, OP, ACT, O>;
+  CX_TRY(once.set(kern, (int)d2_smem_bytes(O)));
+  kern<<<grid, DW2_THREADS, d2_smem_bytes(O), st>>>(bp);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int OP, int ACT>
+static int launch_dw2_o(const BwdParams& bp, int O, int grid, cudaStream_t st) {
+  switch (O) {
+    case 1: return launch_dw2_inst<T, OP, ACT, 1>(bp, grid, st);
+    case 2: return launch_dw2_inst<T, OP, ACT, 2>(bp, grid, st);
+    case 3: return launch_dw2_inst<T, OP, ACT, 3>(bp, grid, st);
+    case 4: return launch_dw2_inst<T, OP, ACT, 4>(bp, grid, st);
+  }
+  return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk backward: out width %s%lld > 4", "", O);
+}
+
+template <typename T>
+static int launch_dw2_t(const BwdParams& bp, int op, int act, int O, int grid, cudaStream_t st) {
+  if (op == COORDX_FUSE_PROD)
+    return act == COORDX_ACT_SINE ? launch_dw2_o<T, COORDX_FUSE_PROD, COORDX_ACT_SINE>(bp, O, grid, st)
+                                  : launch_dw2_o<T, COORDX_FUSE_PROD, COORDX_ACT_RELU>(bp, O, grid, st);
+  return act == COORDX_ACT_SINE ? launch_dw2_o<T, COORDX_FUSE_SUM, COORDX_ACT_SINE>(bp, O, grid, st)
+                                : launch_dw2_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU>(bp, O, grid, st);
+}
+
+int launch_dw2(const BwdParams& bp, int precision, int op, int act, int O, int grid, cudaStream_t st) {
+  if (precision == COORDX_PREC_BF16) return launch_dw2_t<__nv_bfloat16>(bp, op, act, O, grid, st);
+  return launch_dw2_t<__half>(bp, op, act, O, grid, st);
+}
+
+template <typename T, int OP>
+static int launch_dfeat_inst(const BwdParams& bp, int n_cta, cudaStream_t st) {
+  static AttrOnce once;
+  auto kern = trunk_bwd_dfeat_kernel<T, OP>;
+  CX_TRY(once.set(kern, (int)DF_TOTAL));
+  kern<<<n_cta, DF_THREADS, DF_TOTAL, st>>>(bp);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_dfeat(const BwdParams& bp, int precision, int op, int n_cta, cudaStream_t st) {
+  if (precision == COORDX_PREC_BF16)
+    return op == COORDX_FUSE_PROD ? launch_dfeat_inst<__nv_bfloat16, COORDX_FUSE_PROD>(bp, n_cta, st)
+                                  : launch_dfeat_inst<__nv_bfloat16, COORDX_FUSE_SUM>(bp, n_cta, st);
+  return op == COORDX_FUSE_PROD ? launch_dfeat_inst<__half, COORDX_FUSE_PROD>(bp, n_cta, st)
+                                : launch_dfeat_inst<__half, COORDX_FUSE_SUM>(bp, n_cta, st);
+}
+
+}  // namespace tcb
+}  // namespace coordx
