@@ -1515,17 +1515,20 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     const int grid = 2 * (int)min((int64_t)(num_sms() / 2), total);
     a.trace = g_bwd_trace_pass == 0 ? g_bwd_trace : nullptr;
     a.dz_img = pl.reuse ? base + pl.dz_off : nullptr;
-    if (v1)
+    if (v1) {
       CX_TRY((launch_bwd_t<T, true>(a, net->fusion_op, net->act, O, grid, st)));
-    else
-      CX_TRY(launch_dw2(a, precision, net->fusion_op, net->act, O, grid, st));
-    a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
-    if (pl.reuse && !v1) {
-      // ---------------- dfeat pass: BOTH feature gradients from the stored dZ^T tiles, one GEMM per tile
+    } else {
+      // rowvec(o) as 16-bit rows (slab-local index): the dW pass' producers and the dfeat pass read them
       prep_rowvec16_kernel<T><<<(unsigned)cdiv(pl.n_oA * HD, 256), 256, 0, st>>>(feats[0], C == 3 ? feats[1] : nullptr, r0, n1, pl.n_oA,
                                                                                 net->fusion_op, base + pl.rows_off);
       CX_LAUNCH_CHECK();
       a.outer_img = base + pl.rows_off;
+      CX_TRY(launch_dw2(a, precision, net->fusion_op, net->act, O, grid, st));
+      if (!pl.reuse) a.outer_img = nullptr;        // (the recompute passes index their row image differently)
+    }
+    a.trace = g_bwd_trace_pass == 1 ? g_bwd_trace : nullptr;
+    if (pl.reuse && !v1) {
+      // ---------------- dfeat pass: BOTH feature gradients from the stored dZ^T tiles, one GEMM per tile
       a.d_inner = dfeat[C - 1];
       a.trace = nullptr;
       CX_TRY(launch_dfeat(a, precision, net->fusion_op, (int)min((int64_t)num_sms(), total), st));

@@ -32,14 +32,18 @@ constexpr uint32_t D2_H = 0;                               // 3 stages x 4 chunk
 constexpr uint32_t D2_IMG = D2_STAGES * 4 * CH;            // 2 x 16 KB: dZ^T image of a 64-point sub-tile
 constexpr uint32_t D2_BAR = D2_IMG + 2 * CH;
 constexpr uint32_t D2_DOUT = D2_BAR + 256;                 // dout staging: D stages x 128 points x O floats
-constexpr int DW2_THREADS = 18 * 32;                       // 0-7 E1 | 8-15 producers | 16 MMA | 17 image store
+// 0-15 E1 (lane quadrant = warp & 3, 16-point column group = warp >> 2) | 16-23 producers | 24 MMA | 25 image store | 26-27 idle
+// (warps come in groups of four for setmaxnreg).  Launched with 72 registers per thread; E1 gives registers away
+// (64), the producers - 64 registers of inner block each - take them (104), the MMA / store group keeps 32.
+constexpr int DW2_THREADS = 28 * 32;
+constexpr int D2_REGS_E1 = 64, D2_REGS_PROD = 104, D2_REGS_MMA = 32;
 __host__ __device__ constexpr int d2_dout_stages(int O) { return O <= 2 ? 2 : 1; }
 __host__ __device__ constexpr uint32_t d2_smem_bytes(int O) { return D2_DOUT + d2_dout_stages(O) * TILE_M * O * 4; }
 
 struct Bars2 {
   uint32_t full, empty;        // [3] H stage
   uint32_t zfull;              // [2] Z^T sub-tile buffer (G1 commit)
-  uint32_t dzfull;             // [2] dZ^T written by E1 (256 threads): TMEM operand + image chunk
+  uint32_t dzfull;             // [2] dZ^T written by E1 (512 threads): TMEM operand + image chunk
   uint32_t imgempty;           // [2] the bulk store has read the image chunk
   uint32_t dsfull, dsempty;    // [2] dout staging
   uint32_t wfull, dwfull, tmem_slot;
@@ -47,6 +51,26 @@ struct Bars2 {
       : full(b0), empty(b0 + 24), zfull(b0 + 48), dzfull(b0 + 64), imgempty(b0 + 80), dsfull(b0 + 96), dsempty(b0 + 112),
         wfull(b0 + 128), dwfull(b0 + 136), tmem_slot(b0 + 144) {}
 };
+
+// sin(2 pi r) and cos(2 pi r) on r in [-1/2, 1/2] (r = fractional part of the angle in revolutions), two values per
+// packed fp32x2 instruction.  Minimax fits: max error 2.5e-4 (sin, feeds only the dWf sums) and 4.0e-5 (cos, feeds dZ,
+// which is rounded to 16 bits right after).  E1 evaluates HALF of its elements this way and half on the MUFU unit:
+// sin AND cos of every element on the MUFU (16 results / clk / SM) was the floor of the whole pass.
+__device__ __forceinline__ uint64_t f2x(float v) { return ptx::pack_f32x2(v, v); }
+__device__ __forceinline__ void sincos_rev_x2(uint64_t t2, uint64_t& sn, uint64_t& cs) {
+  const uint64_t m2 = ptx::add_f32x2(t2, f2x(12582912.f));            // 1.5 * 2^23: rounds t to the nearest integer
+  const uint64_t n2 = ptx::add_f32x2(m2, f2x(-12582912.f));
+  const uint64_t rr = ptx::fma_f32x2(n2, f2x(-1.f), t2);              // r = t - rint(t)
+  const uint64_t q2 = ptx::mul_f32x2(rr, rr);
+  uint64_t ps = ptx::fma_f32x2(q2, f2x(-56.08980178833008f), f2x(77.93164825439453f));
+  ps = ptx::fma_f32x2(ps, q2, f2x(-41.093868255615234f));
+  ps = ptx::fma_f32x2(ps, q2, f2x(6.27863883972168f));
+  sn = ptx::mul_f32x2(ps, rr);
+  uint64_t pc = ptx::fma_f32x2(q2, f2x(45.64854431152344f), f2x(-82.40443420410156f));
+  pc = ptx::fma_f32x2(pc, q2, f2x(64.67355346679688f));
+  pc = ptx::fma_f32x2(pc, q2, f2x(-19.731046676635742f));
+  cs = ptx::fma_f32x2(pc, q2, f2x(0.9999598264694214f));
+}
 
 template <typename T, int OP, int ACT, int O>
 __global__ void __launch_bounds__(DW2_THREADS, 1)
@@ -58,7 +82,7 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Bars2 B(smem_base + D2_BAR);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + D2_BAR + 144);
-  constexpr int W_PROD = 8, W_MMA = 16, W_STORE = 17;
+  constexpr int W_PROD = 16, W_MMA = 24, W_STORE = 25;
   constexpr int DST = d2_dout_stages(O);
 
   const int h = blockIdx.x & 1;                    // half of the trunk's output features
@@ -69,6 +93,9 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
   const int64_t t_end = total * (cta + 1) / n_cta;
   const int my_tiles = (int)(t_end - t_begin);
   const int n_sub = 2 * my_tiles;
+  const int n_o32 = (int)n_o;
+  const int64_t jb0 = my_tiles > 0 ? t_begin / n_o : 0;
+  const int o0 = my_tiles > 0 ? (int)(t_begin - jb0 * n_o) : 0;
 
   if (warp == W_MMA) {
     if (lane == 0) {
@@ -78,12 +105,12 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
       }
       for (int c = 0; c < 2; ++c) {
         ptx::mbar_init(B.zfull + 8 * c, 1);
-        ptx::mbar_init(B.dzfull + 8 * c, 256);
+        ptx::mbar_init(B.dzfull + 8 * c, 512);
         ptx::mbar_init(B.imgempty + 8 * c, 1);
         ptx::mbar_init(B.dsfull + 8 * c, 128);
-        ptx::mbar_init(B.dsempty + 8 * c, 256);
+        ptx::mbar_init(B.dsempty + 8 * c, 512);
       }
-      ptx::mbar_init(B.wfull, 256);
+      ptx::mbar_init(B.wfull, 512);
       ptx::mbar_init(B.dwfull, 1);
       ptx::fence_mbar_init();
     }
@@ -97,96 +124,97 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
   const uint32_t tmem_base = *tmem_slot_gen;
   const uint32_t tZ = tmem_base, tW = tmem_base + 128, tDW = tmem_base + 256;
 
-  if (warp == W_MMA) {
-    // ============================ MMA issuer ============================
-    if (my_tiles > 0 && ptx::elect_one()) {       // (elect, not lane == 0: see ptx::elect_one)
-      constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 0, 0);    // A = W_h (TMEM, M = n_out), B = H (N = 64 points) K-major
-      constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (TMEM, M = n_out), B = H (N = k_in) MN-major
-      ptx::mbar_wait(B.wfull, 0);
-      ptx::tc_fence_after();
-      int st1 = 0, use1 = 0;                       // H stage / use count of the tile G1 works on
-      int st3 = 0;                                 // ... of the tile G3 works on
-      auto issue_g1 = [&](int s) {
-        const uint32_t zb = s & 1, hh = s & 1;
-        if (hh == 0) {
-          ptx::mbar_wait(B.full + 8 * st1, use1 & 1);
-          ptx::tc_fence_after();
-        }
-        // (no wait for the Z^T buffer: its last reader G3(s-2) is earlier in this thread's in-order tensor pipe)
-        const uint32_t hs = smem_base + D2_H + st1 * 4 * CH + hh * 8192;     // rows 64 hh .. 64 hh + 63 of every chunk
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-          ptx::mma_f16_ts(tZ + zb * 64, tW + k * 8, ptx::umma_desc_k_sw128(hs + (k >> 2) * CH + (k & 3) * 32), id_g1, k != 0);
-        ptx::mma_commit(B.zfull + 8 * zb);
-        if (hh == 1 && ++st1 == D2_STAGES) { st1 = 0; ++use1; }
-      };
-      auto issue_g3 = [&](int s) {
-        const uint32_t zb = s & 1, hh = s & 1;
-        ptx::mbar_wait(B.dzfull + 8 * zb, (s >> 1) & 1);
+  if (warp >= W_MMA) {
+    ptx::setmaxnreg_dec<D2_REGS_MMA>();
+    if (warp == W_MMA) {
+      // ============================ MMA issuer ============================
+      if (my_tiles > 0 && ptx::elect_one()) {     // (elect, not lane == 0: see ptx::elect_one)
+        constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 0, 0);    // A = W_h (TMEM, M = n_out), B = H (N = 64 points) K-major
+        constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (TMEM, M = n_out), B = H (N = k_in) MN-major
+        ptx::mbar_wait(B.wfull, 0);
         ptx::tc_fence_after();
-        const uint32_t hs = smem_base + D2_H + st3 * 4 * CH;
+        int st1 = 0, use1 = 0;                     // H stage / use count of the tile G1 works on
+        int st3 = 0;                               // ... of the tile G3 works on
+        // (a G1 of two N = 32 halves with a commit each took 1.0 k clk instead of 0.54 k: with the A operand in tensor
+        // memory an N = 32 MMA costs the same ~32 clk as an N = 64 one)
+        auto issue_g1 = [&](int s) {
+          const uint32_t zb = s & 1, hh = s & 1;
+          if (hh == 0) {
+            ptx::mbar_wait(B.full + 8 * st1, use1 & 1);
+            ptx::tc_fence_after();
+          }
+          // (no wait for the Z^T buffer: its last reader G3(s-2) is earlier in this thread's in-order tensor pipe)
+          const uint32_t hs = smem_base + D2_H + st1 * 4 * CH + hh * 8192;     // rows 64 hh .. 64 hh + 63 of every chunk
 #pragma unroll
-        for (int j = 0; j < 4; ++j)                // K = 64 points, 16 per step; the two E1 warps of a lane quadrant own 32 columns each
-          ptx::mma_f16_ts(tDW, tZ + zb * 64 + (j >> 1) * 32 + (j & 1) * 8, ptx::umma_desc_mn_sw128(hs + (hh * 4 + j) * 2048, CH), id_g3,
-                          (s | j) != 0);
-        if (hh == 1) {
-          ptx::mma_commit(B.empty + 8 * st3);      // H stage free for the producers
-          if (++st3 == D2_STAGES) st3 = 0;
+          for (int k = 0; k < 16; ++k)
+            ptx::mma_f16_ts(tZ + zb * 64, tW + k * 8, ptx::umma_desc_k_sw128(hs + (k >> 2) * CH + (k & 3) * 32), id_g1, k != 0);
+          ptx::mma_commit(B.zfull + 8 * zb);
+          if (hh == 1 && ++st1 == D2_STAGES) { st1 = 0; ++use1; }
+        };
+        auto issue_g3 = [&](int s) {
+          const uint32_t zb = s & 1, hh = s & 1;
+          ptx::mbar_wait(B.dzfull + 8 * zb, (s >> 1) & 1);
+          trace_stamp(p, 0, s, 2);
+          ptx::tc_fence_after();
+          const uint32_t hs = smem_base + D2_H + st3 * 4 * CH;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)              // K = 64 points, 16 per step: E1 column group j wrote its dZ^T pairs over its first 8 columns
+            ptx::mma_f16_ts(tDW, tZ + zb * 64 + j * 16, ptx::umma_desc_mn_sw128(hs + (hh * 4 + j) * 2048, CH), id_g3, (s | j) != 0);
+          if (hh == 1) {
+            ptx::mma_commit(B.empty + 8 * st3);    // H stage free for the producers
+            if (++st3 == D2_STAGES) st3 = 0;
+          }
+        };
+        // G1(s+1) is issued AHEAD of G3(s): E1 is the longest stage, its input must never queue behind G3
+        issue_g1(0);
+        for (int s = 0; s < n_sub; ++s) {
+          trace_stamp(p, 0, s, 0);
+          if (s + 1 < n_sub) issue_g1(s + 1);
+          trace_stamp(p, 0, s, 1);
+          issue_g3(s);
+          trace_stamp(p, 0, s, 3);
         }
-      };
-      // G1(s+1) is issued AHEAD of G3(s): E1 is the longest stage, its input must never queue behind G3
-      issue_g1(0);
-      for (int s = 0; s < n_sub; ++s) {
-        if (s + 1 < n_sub) issue_g1(s + 1);
-        issue_g3(s);
+        ptx::mma_commit(B.dwfull);
       }
-      ptx::mma_commit(B.dwfull);
-    }
-    __syncwarp();
-  } else if (warp == W_STORE) {
-    // ============================ dZ^T image -> HBM (one 16 KB bulk store per sub-tile) ============================
-    if (p.dz_img != nullptr && my_tiles > 0 && ptx::elect_one()) {
-      for (int s = 0; s < n_sub; ++s) {
-        const int t = s >> 1, hh = s & 1;
-        ptx::mbar_wait(B.dzfull + 8 * (s & 1), (s >> 1) & 1);
-        ptx::bulk_s2g(p.dz_img + (((size_t)(t_begin + t) * 2 + h) * 2 + hh) * CH, smem_base + D2_IMG + (s & 1) * CH, CH);
-        ptx::bulk_commit_group();
-        if (s >= 1) {
-          ptx::bulk_wait_group_read<1>();          // the store of sub-tile s-1 has read its chunk
-          ptx::mbar_arrive(B.imgempty + 8 * ((s - 1) & 1));
+      __syncwarp();
+    } else if (warp == W_STORE) {
+      // ============================ dZ^T image -> HBM (one 16 KB bulk store per sub-tile) ============================
+      if (p.dz_img != nullptr && my_tiles > 0 && ptx::elect_one()) {
+        for (int s = 0; s < n_sub; ++s) {
+          const int t = s >> 1, hh = s & 1;
+          ptx::mbar_wait(B.dzfull + 8 * (s & 1), (s >> 1) & 1);
+          ptx::bulk_s2g(p.dz_img + (((size_t)(t_begin + t) * 2 + h) * 2 + hh) * CH, smem_base + D2_IMG + (s & 1) * CH, CH);
+          ptx::bulk_commit_group();
+          // hand the chunk back as soon as the copy engine has READ it (this thread has nothing else to do): signalled
+          // one store later, E1(s+2) found its chunk free only after every warp had finished sub-tile s+1
+          ptx::bulk_wait_group_read<0>();
+          ptx::mbar_arrive(B.imgempty + 8 * (s & 1));
         }
+        ptx::bulk_wait_group0();
       }
-      ptx::bulk_wait_group0();
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp >= W_PROD) {
+    ptx::setmaxnreg_inc<D2_REGS_PROD>();
     // ============================ producers: H tile (inner block piece in registers) ============================
-    // thread (g = lane, rg = warp - 8) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows 16 rg .. 16 rg + 15
+    // thread (g = lane, rg = warp - 16) owns the 16-byte piece g (k = 8g .. 8g+7) of the 16 rows 16 rg .. 16 rg + 15.
+    // rowvec(o) comes as the 16-bit row image (prep_rowvec16_kernel), one 16-byte load per thread, fetched ONE TILE
+    // AHEAD: with 227 KB of shared memory there is no L1 to prefetch into, and an L2 round trip plus three 64-bit
+    // divisions per tile put ~2 k clk between two H tiles (profiles/r02a_dw2_timeline.txt).
     const int g = lane, rg = warp - W_PROD;
     const int ptid = threadIdx.x - W_PROD * 32;    // 0..255; the first 128 also stage dout
     uint32_t in[16][4];
     int64_t cur_jb = -1;
     int st = 0, use = 0, dsg = 0, dsuse = 0;
+    int64_t jb = jb0;
+    int o_local = o0;
+    const uint4* rv_rows = reinterpret_cast<const uint4*>(p.outer_img) + g;      // row o at + o * 32 (512 B per row)
+    uint4 rv_next = my_tiles > 0 ? __ldg(rv_rows + (size_t)o_local * 32) : make_uint4(0, 0, 0, 0);
     for (int t = 0; t < my_tiles; ++t) {
-      const int64_t tt = t_begin + t;
-      const int64_t jb = tt / n_o;
-      const int64_t o_local = tt - jb * n_o;
-      uint32_t rv[4];
-      {
-        float4 x0, x1;
-        load_rowvec8<OP>(p, p.o_begin + o_local, 8 * g, x0, x1);      // L1 hit: prefetched during the previous tile
-        rv[0] = Pack<T>::pack(x0.x, x0.y);
-        rv[1] = Pack<T>::pack(x0.z, x0.w);
-        rv[2] = Pack<T>::pack(x1.x, x1.y);
-        rv[3] = Pack<T>::pack(x1.z, x1.w);
-      }
-      if (t + 1 < my_tiles) {                      // next tile's rowvec -> L1 while this tile is produced (no registers held)
-        const int64_t tn = tt + 1, jn = tn / n_o;
-        const int64_t on = p.o_begin + (tn - jn * n_o);
-        const int64_t i0 = p.outer1 ? on / p.n_outer1 : on;
-        ptx::prefetch_l1(p.outer0 + i0 * HD + 8 * g);
-        if (p.outer1) ptx::prefetch_l1(p.outer1 + (on - i0 * p.n_outer1) * HD + 8 * g);
-      }
+      const uint4 rv = rv_next;
+      int o_nxt = o_local + 1;
+      if (o_nxt == n_o32) o_nxt = 0;
+      if (t + 1 < my_tiles) rv_next = __ldg(rv_rows + (size_t)o_nxt * 32);       // in flight while this tile is written
       float dreg[O];
 #pragma unroll
       for (int oo = 0; oo < O; ++oo) dreg[oo] = 0.f;
@@ -194,7 +222,7 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
         const int64_t j = jb * TILE_M + ptid;
         if (j < p.n_inner) {
 #pragma unroll
-          for (int oo = 0; oo < O; ++oo) dreg[oo] = __ldg(p.dout + (o_local * p.stride_o + j * p.stride_j) * O + oo);
+          for (int oo = 0; oo < O; ++oo) dreg[oo] = __ldg(p.dout + ((int64_t)o_local * p.stride_o + j * p.stride_j) * O + oo);
         }
       }
       if (jb != cur_jb) {
@@ -224,20 +252,23 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
         }
         cur_jb = jb;
       }
+      if (ptid == 0) trace_stamp(p, 3, t, 0);
       ptx::mbar_wait(B.empty + 8 * st, (use & 1) ^ 1);
+      if (ptid == 0) trace_stamp(p, 3, t, 1);
       uint8_t* dst = smem_gen + D2_H + (uint32_t)st * 4 * CH + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         uint4 w;
-        w.x = fuse2<T, OP>(in[r][0], rv[0]);
-        w.y = fuse2<T, OP>(in[r][1], rv[1]);
-        w.z = fuse2<T, OP>(in[r][2], rv[2]);
-        w.w = fuse2<T, OP>(in[r][3], rv[3]);
+        w.x = fuse2<T, OP>(in[r][0], rv.x);
+        w.y = fuse2<T, OP>(in[r][1], rv.y);
+        w.z = fuse2<T, OP>(in[r][2], rv.z);
+        w.w = fuse2<T, OP>(in[r][3], rv.w);
         *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
       }
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(B.full + 8 * st);
+      if (ptid == 0) trace_stamp(p, 3, t, 2);
       if (++st == D2_STAGES) { st = 0; ++use; }
       if (ptid < TILE_M) {
         ptx::mbar_wait(B.dsempty + 8 * dsg, (dsuse & 1) ^ 1);    // E1 has read the dout that lived in this slot
@@ -247,19 +278,25 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
         ptx::mbar_arrive(B.dsfull + 8 * dsg);
       }
       if (++dsg == DST) { dsg = 0; ++dsuse; }
+      if (ptid == 0) trace_stamp(p, 3, t, 3);
+      o_local = o_nxt;
+      if (o_nxt == 0) ++jb;
     }
   } else {
-    // ============================ E1 (8 warps): Z^T sub-tile -> dZ^T (TMEM operand of G3 + image chunk) ============================
-    // thread = output feature n = 128 h + row; warp (q, pq) covers the 32 points [32 pq, 32 pq + 32) of the 64-point sub-tile.
+    ptx::setmaxnreg_dec<D2_REGS_E1>();
+    // ============================ E1 (16 warps): Z^T sub-tile -> dZ^T (TMEM operand of G3 + image chunk) ============================
+    // thread = output feature n = 128 h + row; warp (q, pq) covers the 16 points [16 pq, 16 pq + 16) of the 64-point sub-tile.
+    // Four E1 warps per scheduler: with two (32 points each) a scheduler issued one sin / cos chain at a time and
+    // reached 75 % of the MUFU rate inside the batch (1039 -> 979 us per 2048^2).
     // bias'[n], wfs[o][n] are registers; db[n] and dWf[o][n] are per-thread running sums (no cross-lane reduction).
     const int q = warp & 3, pq = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     {
-      // W_h row n (this thread's TMEM lane), k in [128 pq, 128 pq + 128): the K-major A operand of G1, 16-bit pairs
-      const float* wrow = p.w_f32 + (size_t)(h * 128 + row) * HD + pq * 128;
+      // W_h row n (this thread's TMEM lane), k in [64 pq, 64 pq + 64): the K-major A operand of G1, 16-bit pairs
+      const float* wrow = p.w_f32 + (size_t)(h * 128 + row) * HD + pq * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t pkw[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -267,7 +304,7 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
           pkw[2 * i] = Pack<T>::pack(v.x, v.y);
           pkw[2 * i + 1] = Pack<T>::pack(v.z, v.w);
         }
-        ptx::tmem_st_32x32b_x16(tW + lane_base + pq * 64 + c * 16, pkw);
+        ptx::tmem_st_32x32b_x16(tW + lane_base + pq * 32 + c * 16, pkw);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -278,51 +315,71 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
     float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]   (times the loss scale)
 #pragma unroll
     for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row] * gscale;
+    constexpr bool PACKED = ACT == COORDX_ACT_SINE && O == 1;     // the headline case: packed fp32x2 arithmetic, half the elements off the MUFU
     float db_acc = 0.f;
     float dwf_acc[O];
 #pragma unroll
     for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = 0.f;
+    uint64_t db2 = 0ull, dwf2 = 0ull;                             // PACKED: (even point, odd point) partial sums
+    const uint64_t S2 = f2x(p.S), B2 = f2x(bias_n);               // angle in radians (MUFU half)
+    const uint64_t S2r = f2x(p.S * 0.15915494309189535f), B2r = f2x(bias_n * 0.15915494309189535f);   // in revolutions (polynomial half)
+    const uint64_t W2 = f2x(wfs_n[0]);
     int dsg = 0, dsuse = 0;
+    const bool tr = q == 0 && lane == 0 && (pq == 0 || pq == 3);
+    const int trole = pq == 0 ? 1 : 2;
     for (int s = 0; s < n_sub; ++s) {
       const int hh = s & 1;
       const uint32_t zb = s & 1;
-      if (warp == 0 && lane == 0) trace_stamp(p, 1, s, 0);
+      if (tr) trace_stamp(p, trole, s, 0);
       if (hh == 0) ptx::mbar_wait(B.dsfull + 8 * dsg, dsuse & 1);
       ptx::mbar_wait(B.zfull + 8 * zb, (s >> 1) & 1);
-      if (warp == 0 && lane == 0) trace_stamp(p, 1, s, 1);
+      if (tr) trace_stamp(p, trole, s, 1);
       ptx::tc_fence_after();
-      const float* ds = reinterpret_cast<const float*>(smem_gen + D2_DOUT) + (dsg * TILE_M + hh * 64 + pq * 32) * O;
-      const uint32_t zaddr = tZ + zb * 64 + pq * 32 + lane_base;
-      uint32_t pk[16];
-      uint32_t ra[16], rb[16];
-      ptx::tmem_ld_32x32b_x16(zaddr, ra);
+      const float* ds = reinterpret_cast<const float*>(smem_gen + D2_DOUT) + (dsg * TILE_M + hh * 64 + pq * 16) * O;
+      const uint32_t zaddr = tZ + zb * 64 + pq * 16 + lane_base;
+      uint32_t pk[8];
+      uint32_t r[16];
+      ptx::tmem_ld_32x32b_x16(zaddr, r);
+      if (PACKED) {
+        uint64_t d2[8];                            // dout of the 16 points as (even, odd) pairs: 4 broadcast LDS.128
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {                // 16 columns (points) per TMEM load, the second in flight during the first's arithmetic
-        uint32_t(&r)[16] = b ? rb : ra;
-        ptx::tmem_ld_wait();
-        if (b == 0) ptx::tmem_ld_32x32b_x16(zaddr + 16, rb);
-        float4 d4[4];                              // O == 1: dout of the batch's 16 points, 4 broadcast LDS.128
-        if (O == 1) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) d4[v] = *reinterpret_cast<const float4*>(ds + b * 16 + v * 4);
+        for (int v = 0; v < 4; ++v) {
+          const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(ds + v * 4);
+          d2[2 * v] = t.x;
+          d2[2 * v + 1] = t.y;
         }
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e2 = 0; e2 < 8; ++e2) {
+          const uint64_t zz = ptx::pack_f32x2(__uint_as_float(r[2 * e2]), __uint_as_float(r[2 * e2 + 1]));
+          uint64_t sn, cs;
+          if (e2 & 1) {                            // polynomial half
+            sincos_rev_x2(ptx::fma_f32x2(zz, S2r, B2r), sn, cs);
+          } else {                                 // MUFU half
+            float th0, th1;
+            ptx::unpack_f32x2(ptx::fma_f32x2(zz, S2, B2), th0, th1);
+            sn = ptx::pack_f32x2(__sinf(th0), __sinf(th1));
+            cs = ptx::pack_f32x2(__cosf(th0), __cosf(th1));
+          }
+          const uint64_t dz = ptx::mul_f32x2(ptx::mul_f32x2(d2[e2], W2), cs);
+          db2 = ptx::add_f32x2(db2, dz);
+          dwf2 = ptx::fma_f32x2(d2[e2], sn, dwf2);
+          float dz0, dz1;
+          ptx::unpack_f32x2(dz, dz0, dz1);
+          pk[e2] = Pack<T>::pack(dz0, dz1);
+        }
+      } else {
+        ptx::tmem_ld_wait();
 #pragma unroll
         for (int e2 = 0; e2 < 8; ++e2) {
           float dz2[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = e2 * 2 + u;
-            const float* dp = ds + (b * 16 + i) * O;              // warp-uniform shared-memory address: broadcast
-            float gw, d0 = 0.f;
-            if (O == 1) {
-              const float4 dv = d4[i >> 2];
-              d0 = (i & 3) == 0 ? dv.x : ((i & 3) == 1 ? dv.y : ((i & 3) == 2 ? dv.z : dv.w));
-              gw = d0 * wfs_n[0];
-            } else {
-              gw = 0.f;
+            const float* dp = ds + i * O;          // warp-uniform shared-memory address: broadcast
+            float gw = 0.f;
 #pragma unroll
-              for (int oo = 0; oo < O; ++oo) gw = fmaf(dp[oo], wfs_n[oo], gw);
-            }
+            for (int oo = 0; oo < O; ++oo) gw = fmaf(dp[oo], wfs_n[oo], gw);
             const float z = __uint_as_float(r[i]);
             float av;                              // activation value (for dWf); the derivative is folded into dz
             if (ACT == COORDX_ACT_SINE) {
@@ -335,53 +392,57 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
               av = fmaxf(pre, 0.f);
             }
             db_acc += dz2[u];
-            if (O == 1) {
-              dwf_acc[0] = fmaf(d0, av, dwf_acc[0]);
-            } else {
 #pragma unroll
-              for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
-            }
+            for (int oo = 0; oo < O; ++oo) dwf_acc[oo] = fmaf(dp[oo], av, dwf_acc[oo]);
           }
-          pk[b * 8 + e2] = Pack<T>::pack(dz2[0], dz2[1]);
+          pk[e2] = Pack<T>::pack(dz2[0], dz2[1]);
         }
       }
+      if (tr) trace_stamp(p, trole, s, 2);
       if (hh == 1) {
         ptx::mbar_arrive(B.dsempty + 8 * dsg);     // last read of this tile's staged dout
         if (++dsg == DST) { dsg = 0; ++dsuse; }
       }
-      // dZ^T goes back into TENSOR MEMORY, over the first 16 of this warp's own 32 Z^T columns (all of them are in
+      // dZ^T goes back into TENSOR MEMORY, over the first 8 of this warp's own 16 Z^T columns (all of them are in
       // registers by now), as the A operand of G3.  No extra barrier: G1(s+2), the next writer of this buffer, is
       // issued after G3(s) in the in-order tensor pipe.
-      ptx::tmem_st_32x32b_x16(zaddr, pk);
+      ptx::tmem_st_32x32b_x8(zaddr, pk);
       if (p.dz_img) {                              // the image for the dfeat pass: shared memory, then one bulk store per sub-tile
         ptx::mbar_wait(B.imgempty + 8 * zb, ((s >> 1) & 1) ^ 1);
         uint8_t* dzrow = smem_gen + D2_IMG + zb * CH;
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc)             // 8 points = one swizzled 16-byte piece of row n
-          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, (pq * 4 + pc) * 8)) =
+        for (int pc = 0; pc < 2; ++pc)             // 8 points = one swizzled 16-byte piece of row n
+          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, (pq * 2 + pc) * 8)) =
               make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
         ptx::fence_proxy_async();
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(B.dzfull + 8 * zb);
-      if (warp == 0 && lane == 0) trace_stamp(p, 1, s, 3);
+      if (tr) trace_stamp(p, trole, s, 3);
     }
     if (my_tiles > 0) {
+      if (PACKED) {
+        float a0, a1;
+        ptx::unpack_f32x2(db2, a0, a1);
+        db_acc = a0 + a1;
+        ptx::unpack_f32x2(dwf2, a0, a1);
+        dwf_acc[0] = a0 + a1;
+      }
       atomicAdd(p.db + h * 128 + row, db_acc * ginv);
 #pragma unroll
       for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
       // ---- flush dW_h (accumulated over every tile of this CTA) with one atomic per element
       ptx::mbar_wait(B.dwfull, 0);
       ptx::tc_fence_after();
-      float* drow = p.dW + (size_t)(h * 128 + row) * HD + pq * 128;
+      float* drow = p.dW + (size_t)(h * 128 + row) * HD + pq * 64;
 #pragma unroll 1
       for (int b = 0; b < 4; ++b) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tDW + lane_base + pq * 128 + b * 32, r);
+        uint32_t rr[16];
+        ptx::tmem_ld_32x32b_x16(tDW + lane_base + pq * 64 + b * 16, rr);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(drow + b * 32 + i, __uint_as_float(r[i]) * ginv);
+        for (int i = 0; i < 16; ++i) atomicAdd(drow + b * 16 + i, __uint_as_float(rr[i]) * ginv);
       }
     }
   }
