@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get('COORDX_B200_LIB') or os.path.join(HERE, 'libcoordx_b2
 MAX_BRANCHES = 4
 MAX_LAYERS = 12
 ACT_SINE, ACT_RELU = 0, 1
+ACTS = {'sine': 0, 'relu': 1, 'sigmoid': 2, 'tanh': 3, 'selu': 4, 'softplus': 5, 'elu': 6}     # COORDX_ACT_*
 FUSE_SUM, FUSE_PROD = 0, 1
 LOSS_MSE, LOSS_BCE = 0, 1
 PREC_FP32, PREC_BF16, PREC_FP16 = 0, 1, 2

@@ -237,11 +237,8 @@ static int launch(const coordx_net* net, int c_begin, int c_end, const float* co
   a.blk0[a.n_branches] = blocks;
   for (int k = 0; k < net->n_pre; ++k) { a.w[k] = net->layer_w[k]; a.b[k] = net->layer_b[k]; }
   if (blocks == 0) return 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(branch_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static AttrOnce once;
+  CX_TRY(once.set(branch_fused_fwd_kernel, (int)SMEM_BYTES));
   branch_fused_fwd_kernel<<<blocks, THREADS, SMEM_BYTES, st>>>(a);
   CX_LAUNCH_CHECK();
   return 0;

@@ -41,6 +41,34 @@ inline int set_err(int code, const char* fmt, const char* a = "", long long b = 
     if (_r != 0) return _r;   \
   } while (0)
 
+// cudaFuncSetAttribute is per DEVICE: one flag per (kernel instantiation, device ordinal).  Use as
+//   static AttrOnce once;  CX_TRY(once.set(kernel, bytes));
+struct AttrOnce {
+  bool done[64] = {};
+  template <typename K>
+  int set(K kern, int bytes) {
+    int dev = 0;
+    CX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return 0;
+  }
+};
+
+// SM count of the CURRENT device (cached per device ordinal)
+static inline int num_sms() {
+  static int cache[64] = {};
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -106,11 +134,45 @@ __device__ __forceinline__ float cos_inl(float x) {
   return ((q + 1) & 2) ? -v : v;
 }
 
+// the remaining entries of the reference's nonlinearity table (modules.py:170-176: nn.Sigmoid, nn.Tanh, nn.SELU,
+// nn.Softplus(beta 1, threshold 20), nn.ELU(alpha 1)): FP32 path only, out of line so that the sine / relu code
+// of every kernel stays as it was
+static __device__ __noinline__ float act_other_fwd(int act, float z) {
+  switch (act) {
+    case COORDX_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+    case COORDX_ACT_TANH: return tanhf(z);
+    case COORDX_ACT_SELU: return 1.0507009873554804934193349852946f * (z > 0.f ? z : 1.6732632423543772848170429916717f * expm1f(z));
+    case COORDX_ACT_SOFTPLUS: return z > 20.f ? z : log1pf(expf(z));
+    case COORDX_ACT_ELU: return z > 0.f ? z : expm1f(z);
+  }
+  return z;
+}
+static __device__ __noinline__ float act_other_grad(int act, float z) {
+  switch (act) {
+    case COORDX_ACT_SIGMOID: {
+      const float s = 1.f / (1.f + expf(-z));
+      return s * (1.f - s);
+    }
+    case COORDX_ACT_TANH: {
+      const float t = tanhf(z);
+      return 1.f - t * t;
+    }
+    case COORDX_ACT_SELU: return 1.0507009873554804934193349852946f * (z > 0.f ? 1.f : 1.6732632423543772848170429916717f * expf(z));
+    case COORDX_ACT_SOFTPLUS: return z > 20.f ? 1.f : 1.f / (1.f + expf(-z));
+    case COORDX_ACT_ELU: return z > 0.f ? 1.f : expf(z);
+  }
+  return 1.f;
+}
+
 __device__ __forceinline__ float act_fwd(int act, float S, float z) {
-  return act == COORDX_ACT_SINE ? sin_inl(S * z) : fmaxf(z, 0.f);
+  if (act == COORDX_ACT_SINE) return sin_inl(S * z);
+  if (act == COORDX_ACT_RELU) return fmaxf(z, 0.f);
+  return act_other_fwd(act, z);
 }
 __device__ __forceinline__ float act_grad(int act, float S, float z) {
-  return act == COORDX_ACT_SINE ? S * cos_inl(S * z) : (z > 0.f ? 1.f : 0.f);
+  if (act == COORDX_ACT_SINE) return S * cos_inl(S * z);
+  if (act == COORDX_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  return act_other_grad(act, z);
 }
 
 }  // namespace coordx

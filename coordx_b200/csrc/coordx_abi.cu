@@ -160,7 +160,7 @@ static int check_net(const coordx_net* net) {
     return set_err(COORDX_ERR_ARG, "bad layer counts%s (n_pre %lld, n_layers %lld)", "", net->n_pre, net->n_layers);
   if (net->fusion_op != COORDX_FUSE_SUM && net->fusion_op != COORDX_FUSE_PROD)
     return set_err(COORDX_ERR_ARG, "unknown fusion operator%s (%lld)", "", net->fusion_op);   // the reference silently skips the fusion (modules.py:336-341)
-  if (net->act != COORDX_ACT_SINE && net->act != COORDX_ACT_RELU) return set_err(COORDX_ERR_ARG, "unknown activation%s (%lld)", "", net->act);
+  if (net->act < COORDX_ACT_SINE || net->act > COORDX_ACT_ELU) return set_err(COORDX_ERR_ARG, "unknown activation%s (%lld)", "", net->act);
   if (net->hidden <= 0 || net->fuse_width % net->hidden != 0) return set_err(COORDX_ERR_ARG, "fuse_width must be a multiple of hidden%s");
   return 0;
 }
@@ -217,26 +217,87 @@ static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backw
 }
 
 // ------------------------------------------------------------------ trunk planning (fp32 path)
+// The [P, Hd] fused tensor is built chunk by chunk inside the workspace.  A chunk is a box of the grid that is
+// CONTIGUOUS in the row-major output: a single index on every axis before `axis`, `step` consecutive samples of
+// `axis`, and all of the axes after it - whole axis-0 rows for image-sized grids (axis = 0), pieces of one row when
+// a single row is already longer than the target (a 1 x P scattered "grid", a 3-D grid with a large n1 * n2).
 struct TrunkPlan {
-  int64_t inner;        // prod_{c>0} n_c
-  int64_t chunk_rows;   // whole axis-0 rows per chunk
-  int64_t chunk_pts;
+  int axis;             // the axis that is cut into pieces
+  int64_t step;         // samples of `axis` per chunk
+  int64_t chunk_pts;    // points of a full chunk: the workspace is sized for this many
 };
 
 static TrunkPlan plan_trunk(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1) {
-  TrunkPlan pl{};
-  pl.inner = 1;
-  for (int c = 1; c < net->n_branches; ++c) pl.inner *= n[c];
+  const int C = net->n_branches;
   const int64_t target = 32768;      // points per chunk: [chunk, 256] fp32 = 32 MB, stays L2-resident
-  pl.chunk_rows = max((int64_t)1, min(r1 - r0, target / max(pl.inner, (int64_t)1)));
-  pl.chunk_pts = pl.chunk_rows * pl.inner;
+  TrunkPlan pl{};
+  int64_t below = 1;                 // prod of the extents of the axes after `axis`
+  pl.axis = C - 1;
+  for (int c = C - 1; c >= 0; --c) {
+    const int64_t ext = c == 0 ? r1 - r0 : n[c];
+    pl.axis = c;
+    if (below * ext > target || c == 0) break;
+    below *= ext;
+  }
+  const int64_t ext_a = pl.axis == 0 ? r1 - r0 : n[pl.axis];
+  pl.step = max((int64_t)1, min(ext_a, target / max(below, (int64_t)1)));
+  pl.chunk_pts = pl.step * below;
   return pl;
 }
 
-static FuseArgs make_fuse_args(const coordx_net* net, const float* const* feats, const int64_t* n, const TrunkPlan& pl) {
+// one chunk of the plan as a sub-grid of its own: offset table pointers, per-axis counts, position in the output
+struct TrunkChunk {
+  const float* feats[COORDX_MAX_BRANCHES];
+  float* dfeat[COORDX_MAX_BRANCHES];
+  int64_t n[COORDX_MAX_BRANCHES];
+  int64_t first_pt;     // index of the chunk's first point inside the slab's output
+  int64_t pts;
+};
+
+// enumerate the chunks in output order; fn(const TrunkChunk&) returns 0 or an error code
+template <typename Fn>
+static int for_each_chunk(const coordx_net* net, const TrunkPlan& pl, const float* const* feats, float* const* dfeat,
+                          const int64_t* n, int64_t r0, int64_t r1, Fn fn) {
+  const int C = net->n_branches, F = net->fuse_width;
+  int64_t idx[COORDX_MAX_BRANCHES] = {};          // current index on the axes before pl.axis (axis 0 relative to r0)
+  auto ext = [&](int c) { return c == 0 ? r1 - r0 : n[c]; };
+  for (;;) {
+    for (int64_t i0 = 0; i0 < ext(pl.axis); i0 += pl.step) {
+      TrunkChunk ch{};
+      int64_t lin = 0;
+      ch.pts = 1;
+      for (int c = 0; c < C; ++c) {
+        const int64_t start = c < pl.axis ? idx[c] : (c == pl.axis ? i0 : 0);
+        const int64_t cnt = c < pl.axis ? 1 : (c == pl.axis ? min(pl.step, ext(c) - i0) : ext(c));
+        const int64_t abs0 = start + (c == 0 ? r0 : 0);
+        ch.feats[c] = feats[c] + abs0 * F;
+        ch.dfeat[c] = dfeat ? dfeat[c] + abs0 * F : nullptr;
+        ch.n[c] = cnt;
+        ch.pts *= cnt;
+        lin = lin * ext(c) + start;
+      }
+      ch.first_pt = lin;
+      CX_TRY(fn(ch));
+    }
+    int c = pl.axis - 1;                           // odometer over the axes before pl.axis
+    for (; c >= 0; --c) {
+      if (++idx[c] < ext(c)) break;
+      idx[c] = 0;
+    }
+    if (c < 0) break;
+  }
+  return 0;
+}
+
+static FuseArgs make_fuse_args(const coordx_net* net, const TrunkChunk& ch) {
   FuseArgs a{};
   a.C = net->n_branches;
-  for (int c = 0; c < a.C; ++c) { a.feat[c] = feats[c]; a.n[c] = n[c]; }
+  a.inner = 1;
+  for (int c = 0; c < a.C; ++c) {
+    a.feat[c] = ch.feats[c];
+    a.n[c] = ch.n[c];
+    if (c > 0) a.inner *= ch.n[c];
+  }
   a.F = net->fuse_width;
   a.Hd = net->hidden;
   a.gs = net->fuse_width / net->hidden;
@@ -245,7 +306,8 @@ static FuseArgs make_fuse_args(const coordx_net* net, const float* const* feats,
   a.act = net->act;
   a.S = 30.f * net->act_scale;
   a.code = net->has_code ? net->code : nullptr;
-  a.inner = pl.inner;
+  a.row0 = 0;
+  a.nrows = ch.n[0];
   return a;
 }
 
@@ -391,7 +453,7 @@ size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int
     return sep::workspace_bytes(net, n, row_begin, row_end, backward != 0);
   if (precision != COORDX_PREC_FP32) {
     if (!tc::tc_supported(net, precision)) return 0;
-    if (backward) return tc::bwd_workspace_bytes(net, n, row_begin, row_end) + 1024;
+    if (backward) return tc::bwd_workspace_bytes(net, n, row_begin, row_end, backward == 2) + 1024;
     return tc::fwd_workspace_bytes(n[net->n_branches - 1]) + 1024;
   }
   const TrunkPlan pl = plan_trunk(net, n, row_begin, row_end);
@@ -431,21 +493,18 @@ int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const
   ChainWs w{};
   if (nl > 0) carve_chain(ar, L, nl, pl.chunk_pts, false, w);
   if (!ws || !ar.ok()) return set_err(COORDX_ERR_WORKSPACE, "trunk forward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
-  FuseArgs fa = make_fuse_args(net, feats, n, pl);
   const float S = 30.f * net->act_scale;
   const int ow = nl > 0 ? L[nl - 1].out : net->hidden;
-  for (int64_t r = row_begin; r < row_end; r += pl.chunk_rows) {
-    const int64_t rows = min(pl.chunk_rows, row_end - r);
-    const int64_t pts = rows * pl.inner;
-    fa.row0 = r;
-    fa.nrows = rows;
-    float* o = out + (r - row_begin) * pl.inner * ow;
+  return for_each_chunk(net, pl, feats, nullptr, n, row_begin, row_end, [&](const TrunkChunk& ch) -> int {
+    const FuseArgs fa = make_fuse_args(net, ch);
+    const int64_t pts = ch.pts;
+    float* o = out + ch.first_pt * ow;
     float* h0 = nl > 0 ? H0 : o;            // approx_layers == num_hidden_layers+1: the fused value is the output
     fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, h0);
     CX_LAUNCH_CHECK();
     if (nl > 0) CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, o, nullptr, nullptr, w.tmp0, w.tmp1, S, st));
-  }
-  return 0;
+    return 0;
+  });
 }
 
 int coordx_trunk_backward(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
@@ -481,16 +540,13 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
   ChainWs w{};
   if (nl > 0) carve_chain(ar, L, nl, pl.chunk_pts, true, w);
   if (!ws || !ar.ok()) return set_err(COORDX_ERR_WORKSPACE, "trunk backward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)ar.off);
-  FuseArgs fa = make_fuse_args(net, feats, n, pl);
   const float S = 30.f * net->act_scale;
   const int ow = nl > 0 ? L[nl - 1].out : net->hidden;
   const int C = net->n_branches;
-  for (int64_t r = row_begin; r < row_end; r += pl.chunk_rows) {
-    const int64_t rows = min(pl.chunk_rows, row_end - r);
-    const int64_t pts = rows * pl.inner;
-    fa.row0 = r;
-    fa.nrows = rows;
-    const float* dY = dout + (r - row_begin) * pl.inner * ow;
+  return for_each_chunk(net, pl, feats, dfeat, n, row_begin, row_end, [&](const TrunkChunk& ch) -> int {
+    const FuseArgs fa = make_fuse_args(net, ch);
+    const int64_t pts = ch.pts;
+    const float* dY = dout + ch.first_pt * ow;
     const float* dh = dY;
     if (nl > 0) {
       fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, H0);
@@ -500,20 +556,21 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
       dh = dH0;
     }
     for (int b = 0; b < C; ++b) {
-      const int64_t cnt_b = b == 0 ? rows : n[b];
+      const int64_t cnt_b = ch.n[b];
       const int64_t T = pts / cnt_b;
       // spread the reduction over the chip: ~4 waves of 128-thread blocks
       const int64_t base_blocks = cdiv(net->fuse_width, 128) * cnt_b;
       int64_t splits = max((int64_t)1, min(cdiv(T, 64), cdiv((int64_t)148 * 16, base_blocks)));
       const int64_t tpb = cdiv(T, splits);
       splits = cdiv(T, tpb);
-      dim3 grid((unsigned)cnt_b, (unsigned)cdiv(net->fuse_width, 128), (unsigned)splits);
       if (splits > 65535) return set_err(COORDX_ERR_UNSUPPORTED, "axis too long for fuse_bwd grid%s (%lld)", "", cnt_b);
-      fuse_bwd_kernel<<<grid, 128, 0, st>>>(fa, b, dh, dfeat[b], (b == 0 && net->has_code) ? grads->code : nullptr, T, tpb);
+      // (gridDim.x carries the samples of axis b: up to 2^31 - 1)
+      dim3 grid((unsigned)cnt_b, (unsigned)cdiv(net->fuse_width, 128), (unsigned)splits);
+      fuse_bwd_kernel<<<grid, 128, 0, st>>>(fa, b, dh, ch.dfeat[b], (b == 0 && net->has_code) ? grads->code : nullptr, T, tpb);
       CX_LAUNCH_CHECK();
     }
-  }
-  return 0;
+    return 0;
+  });
 }
 
 // -------------------------------------------------------------------------- loss / optimiser

@@ -269,6 +269,7 @@ static int tile_n(const Args& a) {
   // ReLU layers stay on the FFMA kernel: its pre-activations differ from the reference's by ~1e-7 relative, the 3xTF32
   // ones by ~2e-6, and every pre-activation that changes sign flips a ReLU gate (a 1/P-sized jump in the gradients)
   if (a.act == COORDX_ACT_RELU && !a.zprev) return 0;
+  if (a.act > COORDX_ACT_RELU) return 0;          // sigmoid / tanh / selu / softplus / elu: FFMA kernels only
   if ((a.lda & 3) || (a.ldb & 3)) return 0;
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return 0;
   const int64_t work = (int64_t)a.M * a.N * a.K;
@@ -280,11 +281,8 @@ static bool usable(const Args& a) { return tile_n(a) != 0; }
 
 template <int BN>
 static int launch_bn(const Args& a, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BN>::SM_TOTAL));
-    attr_done = true;
-  }
+  static AttrOnce once;
+  CX_TRY(once.set(gemm_tf32x3_kernel<BN>, (int)Cfg<BN>::SM_TOTAL));
   dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, BM));
   gemm_tf32x3_kernel<BN><<<grid, THREADS, Cfg<BN>::SM_TOTAL, st>>>(a);
   CX_LAUNCH_CHECK();

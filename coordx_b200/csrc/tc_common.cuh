@@ -30,9 +30,12 @@ template <>
 struct Pack<__half> {
   using V2 = __half2;
   static constexpr uint32_t kFmt = 0;
+  // fp16 saturates instead of overflowing (cvt.satfinite): an unnormalised ReLU feature beyond 65504 becomes the
+  // largest finite value, not an inf that the product fusion and the MMA would turn into NaN
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
-    __half2 v = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t v;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(b), "f"(a));
+    return v;
   }
   static __device__ __forceinline__ float unpack(uint32_t v, int hi) {
     const __half2 h = *reinterpret_cast<const __half2*>(&v);
@@ -45,18 +48,12 @@ __device__ __forceinline__ uint32_t fuse2(uint32_t x, uint32_t y) {
   using V2 = typename Pack<T>::V2;
   V2 a = *reinterpret_cast<V2*>(&x), b = *reinterpret_cast<V2*>(&y);
   V2 r = OP == COORDX_FUSE_PROD ? __hmul2(a, b) : __hadd2(a, b);
-  return *reinterpret_cast<uint32_t*>(&r);
-}
-
-static inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  if (Pack<T>::kFmt == 0) {     // fp16: clamp the fused value to the finite range as well (bf16 has fp32's exponent)
+    const uint32_t hi = 0x7bff7bffu, lo = 0xfbfffbffu;      // +-65504 in both halves
+    asm("min.f16x2 %0, %0, %1;" : "+r"(*reinterpret_cast<uint32_t*>(&r)) : "r"(hi));
+    asm("max.f16x2 %0, %0, %1;" : "+r"(*reinterpret_cast<uint32_t*>(&r)) : "r"(lo));
   }
-  return n;
+  return *reinterpret_cast<uint32_t*>(&r);
 }
 
 // ---- entry points of the two tcgen05 translation units (called from coordx_abi.cu)
@@ -69,7 +66,7 @@ void profile_set_trace(void* dev_buf);
 void profile_set_bwd_trace(void* dev_buf, int pass);
 int profile_last_ms(float* ms_host);
 
-size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1);
+size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1, bool minimal);
 int trunk_backward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
                       const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws,
                       size_t ws_bytes, cudaStream_t st);

@@ -1340,20 +1340,14 @@ pair_scatter_kernel(const float* __restrict__ drv, const float* __restrict__ t0,
 // ---------------------------------------------------------------------------------
 template <typename T, int OP, int ACT, int O, bool DO_DW>
 static int launch_bwd_inst(const BwdParams& bp, int grid, cudaStream_t st) {
-  static bool attr_done = false;
+  static AttrOnce once;
   if (DO_DW) {
     auto kern = trunk_bwd_dw_kernel<T, OP, ACT, O>;
-    if (!attr_done) {
-      CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL_B));
-      attr_done = true;
-    }
+    CX_TRY(once.set(kern, (int)SM_TOTAL_B));
     kern<<<grid, DW_THREADS, SM_TOTAL_B, st>>>(bp);
   } else {
     auto kern = trunk_bwd_dh_kernel<T, OP, ACT, O>;
-    if (!attr_done) {
-      CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL_B));
-      attr_done = true;
-    }
+    CX_TRY(once.set(kern, (int)SM_TOTAL_B));
     kern<<<grid, DH_THREADS, SM_TOTAL_B, st>>>(bp);
   }
   CX_LAUNCH_CHECK();
@@ -1382,12 +1376,9 @@ static int launch_bwd_t(const BwdParams& bp, int op, int act, int O, int grid, c
 
 template <typename T>
 static int launch_drv(const BwdParams& bp, int op, int grid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_drv_kernel<T, COORDX_FUSE_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMR_TOTAL));
-    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_drv_kernel<T, COORDX_FUSE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMR_TOTAL));
-    attr_done = true;
-  }
+  static AttrOnce once_p, once_s;
+  CX_TRY(once_p.set(trunk_bwd_drv_kernel<T, COORDX_FUSE_PROD>, (int)SMR_TOTAL));
+  CX_TRY(once_s.set(trunk_bwd_drv_kernel<T, COORDX_FUSE_SUM>, (int)SMR_TOTAL));
   if (op == COORDX_FUSE_PROD)
     trunk_bwd_drv_kernel<T, COORDX_FUSE_PROD><<<grid, DRV_THREADS, SMR_TOTAL, st>>>(bp);
   else
@@ -1398,12 +1389,9 @@ static int launch_drv(const BwdParams& bp, int op, int grid, cudaStream_t st) {
 
 template <typename T>
 static int launch_din(const BwdParams& bp, int op, int grid, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_din_kernel<T, COORDX_FUSE_PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMI_TOTAL));
-    CX_CUDA(cudaFuncSetAttribute(trunk_bwd_din_kernel<T, COORDX_FUSE_SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMI_TOTAL));
-    attr_done = true;
-  }
+  static AttrOnce once_p, once_s;
+  CX_TRY(once_p.set(trunk_bwd_din_kernel<T, COORDX_FUSE_PROD>, (int)SMI_TOTAL));
+  CX_TRY(once_s.set(trunk_bwd_din_kernel<T, COORDX_FUSE_SUM>, (int)SMI_TOTAL));
   if (op == COORDX_FUSE_PROD)
     trunk_bwd_din_kernel<T, COORDX_FUSE_PROD><<<grid, DIN_THREADS, SMI_TOTAL, st>>>(bp);
   else
@@ -1412,20 +1400,33 @@ static int launch_din(const BwdParams& bp, int op, int grid, cudaStream_t st) {
   return 0;
 }
 
-// dZ^T tiles kept between the dW pass and the d-rowvec pass (64 KB per 128-point tile): on unless
-// COORDX_BWD_DZ_REUSE=0 or the tiles would need more than COORDX_BWD_DZ_MAX_GB (default 24) of workspace
-static bool dz_reuse(int64_t tiles) {
+// dZ^T tiles kept between the dW pass and the feature-gradient pass (64 KB per 128-point tile).  The caller decides
+// by the workspace it provides: coordx_trunk_workspace_bytes(.., backward = 1) asks for the tiles unless
+// COORDX_BWD_DZ_REUSE=0 or they would need more than COORDX_BWD_DZ_MAX_GB (default: 24 GB, at most a quarter of the
+// device's memory); backward = 2 is the size WITHOUT them (the recompute passes), which trunk_backward_tc accepts
+// as well - the host glue falls back to it when the large allocation fails.
+static bool dz_reuse_wanted(int64_t tiles) {
   const char* e = getenv("COORDX_BWD_DZ_REUSE");
   if (e && e[0] == '0') return false;
   const char* m = getenv("COORDX_BWD_DZ_MAX_GB");
-  const double max_gb = m ? atof(m) : 24.0;
-  return (double)tiles * (4.0 * CH) <= max_gb * 1e9;
+  double max_bytes = (m ? atof(m) : 24.0) * 1e9;
+  if (!m) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) max_bytes = fmin(max_bytes, 0.25 * (double)total_b);
+    else (void)cudaGetLastError();
+  }
+  return (double)tiles * (4.0 * CH) <= max_bytes;
 }
 
 // COORDX_BWD_V1=1: the first-generation kernels (dW pass with W_h in shared memory, separate drv and din passes): A/B timing only
 static bool bwd_v1() {
   const char* e = getenv("COORDX_BWD_V1");
   return e && e[0] == '1';
+}
+
+static bool bwd_recompute_forced() {
+  const char* e = getenv("COORDX_BWD_DZ_REUSE");
+  return e && e[0] == '0';
 }
 
 static long long* g_bwd_trace = nullptr;
@@ -1438,7 +1439,7 @@ struct BwdPlan {
   int64_t n_innerA, n_innerB, n_oA;
 };
 
-static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1) {
+static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1, bool reuse) {
   const int C = net->n_branches;
   BwdPlan pl{};
   pl.n_innerA = n[C - 1];
@@ -1454,7 +1455,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   pl.innerB_off = off; off += (size_t)pl.nbB * INNER_BYTES;
   pl.drv_off = off; off += C == 3 ? align_up((size_t)pl.n_oA * HD * 4, 1024) : 0;
   pl.rows_off = off; off += align_up((size_t)max(pl.n_innerA, pl.n_oA) * HD * 2, 1024);   // 16-bit rowvec rows (din pass / pass B)
-  pl.reuse = dz_reuse((int64_t)pl.nbA * pl.n_oA);
+  pl.reuse = reuse;
   pl.dz_off = off; off += pl.reuse ? (size_t)pl.nbA * pl.n_oA * (4 * CH) : 0;
   pl.total = off;
   return pl;
@@ -1465,7 +1466,8 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
                                const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws, size_t ws_bytes,
                                cudaStream_t st) {
   const int C = net->n_branches, L = net->n_pre, O = net->layer_out[L + 1];
-  const BwdPlan pl = plan_bwd(net, n, r0, r1);
+  BwdPlan pl = plan_bwd(net, n, r0, r1, true);     // the stored-dZ path if the caller's workspace holds the tiles
+  if (ws_bytes < pl.total || bwd_recompute_forced()) pl = plan_bwd(net, n, r0, r1, false);
   if (!ws || ws_bytes < pl.total) return set_err(COORDX_ERR_WORKSPACE, "tcgen05 trunk backward: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)pl.total);
   uint8_t* base = (uint8_t*)ws;
   uint8_t* w_img = base + pl.w_img_off;
@@ -1588,7 +1590,11 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
 namespace coordx {
 namespace tc {
 void profile_set_bwd_trace(void* dev_buf, int pass) { tcb::g_bwd_trace = (long long*)dev_buf; tcb::g_bwd_trace_pass = pass; }
-size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1) { return tcb::plan_bwd(net, n, r0, r1).total; }
+size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1, bool minimal) {
+  const tcb::BwdPlan small = tcb::plan_bwd(net, n, r0, r1, false);
+  if (minimal || !tcb::dz_reuse_wanted((int64_t)small.nbA * small.n_oA)) return small.total;
+  return tcb::plan_bwd(net, n, r0, r1, true).total;
+}
 int trunk_backward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
                       const float* dout, coordx_grads* grads, float* const* dfeat, int precision, void* ws,
                       size_t ws_bytes, cudaStream_t st) {

@@ -31,9 +31,24 @@
 //   warp 16     TMEM alloc; in the LEADER CTA one lane issues tcgen05.mma.cta_group::2 for the pair
 //   warps 17-19 idle (complete the warpgroup that gives its registers away)
 // Shared memory: W half 64 KB (resident) | A ring 2 x 64 KB (whole tiles, 4 K-chunks of 64 each).
+//
+// This file is compiled EPI_COPIES times (-DCOORDX_FWD_COPY=k, coordx_b200/build.py): the epilogue reads the trunk
+// bias and the final layer as constant-bank operands with compile-time offsets (a runtime slot index turns the
+// 16-byte uniform loads into twice as many 8-byte ones and costs 10 % of the kernel, measured), so every copy of the
+// kernel owns one `__constant__` image.  Launches take the copies round-robin: forwards of different nets on
+// different streams, or in different captured graphs, do not overwrite each other's constants.  Copy 0 also holds
+// the host side.
 #include <type_traits>
+#include <mutex>
 
 #include "tc_common.cuh"
+
+#ifndef COORDX_FWD_COPY
+#define COORDX_FWD_COPY 0
+#endif
+#define CX_CAT2(a, b) a##b
+#define CX_CAT(a, b) CX_CAT2(a, b)
+#define FWD_COPY_NS CX_CAT(fwd_copy, COORDX_FWD_COPY)
 
 namespace coordx {
 namespace tc {
@@ -64,19 +79,6 @@ struct EpiConst {
   float wf[MAX_O][HD];       // final layer weight
   float bf[MAX_O];
 };
-__constant__ EpiConst c_epi;
-
-__global__ void __launch_bounds__(256)
-prep_epi_kernel(const float* __restrict__ b, const float* __restrict__ Wf, const float* __restrict__ bf, int O, int act,
-                float S, EpiConst* __restrict__ epi) {
-  const int idx = blockIdx.x * 256 + threadIdx.x;          // over MAX_O * 256
-  if (idx < HD) epi->bias[idx] = act == COORDX_ACT_SINE ? S * b[idx] : b[idx];
-  if (idx < MAX_O * HD) {
-    const int o = idx >> 8;
-    epi->wf[o][idx & 255] = o < O ? Wf[idx] : 0.f;
-  }
-  if (idx < MAX_O) epi->bf[idx] = idx < O ? bf[idx] : 0.f;
-}
 
 // ---------------------------------------------------------------------------------
 struct FwdParams {
@@ -93,6 +95,9 @@ struct FwdParams {
   long long* trace;         // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
 };
 constexpr int TRACE_ITERS = 96;
+
+namespace FWD_COPY_NS {
+__constant__ EpiConst c_epi;     // this copy's image of the epilogue constants
 
 // sin(2 pi t) for the "polynomial" share of the epilogue's columns (SINE only).  The MUFU unit evaluates
 // 16 sin/clk/SM - exactly one 128 x 256 tile per 2048 clk, the tcgen05 time of the same tile - so an
@@ -509,6 +514,77 @@ trunk_fwd_tc_kernel(const FwdParams p) {
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+
+// columns per 32 that take MUFU.SIN; the polynomial share is only used with bf16 operands, whose own
+// rounding already dominates the error (fp16 operands keep the exact path)
+template <typename T> struct MufuCols { static constexpr int value = 32; };
+template <> struct MufuCols<__nv_bfloat16> { static constexpr int value = COORDX_FWD_MUFU_COLS; };
+
+template <typename T, int OP, int ACT, int O>
+static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
+  auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, (ACT == COORDX_ACT_SINE ? MufuCols<T>::value : 32)>;
+  static AttrOnce once;
+  CX_TRY(once.set(kern, (int)SMEM_ALLOC));
+  kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int OP, int ACT>
+static int launch_fwd_o(const FwdParams& fp, int O, int grid, cudaStream_t st) {
+  switch (O) {
+    case 1: return launch_fwd_inst<T, OP, ACT, 1>(fp, grid, st);
+    case 2: return launch_fwd_inst<T, OP, ACT, 2>(fp, grid, st);
+    case 3: return launch_fwd_inst<T, OP, ACT, 3>(fp, grid, st);
+    case 4: return launch_fwd_inst<T, OP, ACT, 4>(fp, grid, st);
+  }
+  return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk: out width %s%lld > 4", "", O);
+}
+
+template <typename T>
+static int launch_fwd_t(const FwdParams& fp, int op, int act, int O, int grid, cudaStream_t st) {
+  if (op == COORDX_FUSE_PROD)
+    return act == COORDX_ACT_SINE ? launch_fwd_o<T, COORDX_FUSE_PROD, COORDX_ACT_SINE>(fp, O, grid, st)
+                                  : launch_fwd_o<T, COORDX_FUSE_PROD, COORDX_ACT_RELU>(fp, O, grid, st);
+  return act == COORDX_ACT_SINE ? launch_fwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_SINE>(fp, O, grid, st)
+                                : launch_fwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU>(fp, O, grid, st);
+}
+
+}  // namespace FWD_COPY_NS
+
+// entry of this copy: load its constant image from `epi_dev` (device memory, stream-ordered), launch its kernel
+#define FWD_COPY_ENTRY CX_CAT(trunk_fwd_launch_copy, COORDX_FWD_COPY)
+// (ev_start: optional event recorded between the two - the profiling hook times the kernel alone)
+int FWD_COPY_ENTRY(const FwdParams& fp, const EpiConst* epi_dev, int precision, int op, int act, int O, int grid, cudaStream_t st,
+                   cudaEvent_t ev_start) {
+  CX_CUDA(cudaMemcpyToSymbolAsync(FWD_COPY_NS::c_epi, epi_dev, sizeof(EpiConst), 0, cudaMemcpyDeviceToDevice, st));
+  if (ev_start) CX_CUDA(cudaEventRecord(ev_start, st));
+  if (precision == COORDX_PREC_BF16) return FWD_COPY_NS::launch_fwd_t<__nv_bfloat16>(fp, op, act, O, grid, st);
+  return FWD_COPY_NS::launch_fwd_t<__half>(fp, op, act, O, grid, st);
+}
+
+#if COORDX_FWD_COPY == 0
+// =================================================================================
+// host side (copy 0 only)
+// =================================================================================
+constexpr int EPI_COPIES = 4;            // keep in step with coordx_b200/build.py
+int trunk_fwd_launch_copy1(const FwdParams&, const EpiConst*, int, int, int, int, int, cudaStream_t, cudaEvent_t);
+int trunk_fwd_launch_copy2(const FwdParams&, const EpiConst*, int, int, int, int, int, cudaStream_t, cudaEvent_t);
+int trunk_fwd_launch_copy3(const FwdParams&, const EpiConst*, int, int, int, int, int, cudaStream_t, cudaEvent_t);
+
+static __global__ void __launch_bounds__(256)
+prep_epi_kernel(const float* __restrict__ b, const float* __restrict__ Wf, const float* __restrict__ bf, int O, int act,
+                float S, EpiConst* __restrict__ epi) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;          // over MAX_O * 256
+  if (idx < HD) epi->bias[idx] = act == COORDX_ACT_SINE ? S * b[idx] : b[idx];
+  if (idx < MAX_O * HD) {
+    const int o = idx >> 8;
+    epi->wf[o][idx & 255] = o < O ? Wf[idx] : 0.f;
+  }
+  if (idx < MAX_O) epi->bf[idx] = idx < O ? bf[idx] : 0.f;
+}
+
+
 struct FwdPlan {
   size_t epi_off, total;
   int nb;
@@ -538,51 +614,17 @@ int profile_last_ms(float* ms_host) {
 }
 size_t fwd_workspace_bytes(int64_t n_inner) { return plan_fwd(n_inner).total; }
 
-// columns per 32 that take MUFU.SIN; the polynomial share is only used with bf16 operands, whose own
-// rounding already dominates the error (fp16 operands keep the exact path)
-template <typename T> struct MufuCols { static constexpr int value = 32; };
-template <> struct MufuCols<__nv_bfloat16> { static constexpr int value = COORDX_FWD_MUFU_COLS; };
-
-template <typename T, int OP, int ACT, int O>
-static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
-  auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, (ACT == COORDX_ACT_SINE ? MufuCols<T>::value : 32)>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
-    attr_done = true;
-  }
-  if (g_profile) {
-    if (!g_prof_ev[0]) {
-      CX_CUDA(cudaEventCreate(&g_prof_ev[0]));
-      CX_CUDA(cudaEventCreate(&g_prof_ev[1]));
-    }
-    CX_CUDA(cudaEventRecord(g_prof_ev[0], st));
-  }
-  kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);      // cluster shape (2,1,1) is a compile-time attribute of the kernel
-  CX_LAUNCH_CHECK();
-  if (g_profile) CX_CUDA(cudaEventRecord(g_prof_ev[1], st));
-  return 0;
-}
-
-template <typename T, int OP, int ACT>
-static int launch_fwd_o(const FwdParams& fp, int O, int grid, cudaStream_t st) {
-  switch (O) {
-    case 1: return launch_fwd_inst<T, OP, ACT, 1>(fp, grid, st);
-    case 2: return launch_fwd_inst<T, OP, ACT, 2>(fp, grid, st);
-    case 3: return launch_fwd_inst<T, OP, ACT, 3>(fp, grid, st);
-    case 4: return launch_fwd_inst<T, OP, ACT, 4>(fp, grid, st);
-  }
-  return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk: out width %s%lld > 4", "", O);
-}
-
-template <typename T>
-static int launch_fwd_t(const FwdParams& fp, int op, int act, int O, int grid, cudaStream_t st) {
-  if (op == COORDX_FUSE_PROD)
-    return act == COORDX_ACT_SINE ? launch_fwd_o<T, COORDX_FUSE_PROD, COORDX_ACT_SINE>(fp, O, grid, st)
-                                  : launch_fwd_o<T, COORDX_FUSE_PROD, COORDX_ACT_RELU>(fp, O, grid, st);
-  return act == COORDX_ACT_SINE ? launch_fwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_SINE>(fp, O, grid, st)
-                                : launch_fwd_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU>(fp, O, grid, st);
-}
+// Who used a copy's constant image last (per device): an eager launch on ANOTHER stream waits for that kernel before
+// it overwrites the image.  Captured launches are ordered by their graph; they neither wait on nor record these
+// events (an event recorded inside a capture belongs to the capture).
+struct CopyState {
+  cudaEvent_t done = nullptr;
+  cudaStream_t last = nullptr;
+  bool recorded = false;
+};
+static CopyState g_copy_state[64][EPI_COPIES];
+static std::mutex g_copy_mutex;
+static unsigned g_next_copy = 0;
 
 // feats: C tables [n_c, 256] fp32.  The last axis is the inner axis; axes 0..C-2 are outer.
 int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
@@ -595,10 +637,6 @@ int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int
   if (ws_bytes < pl.total || ws == nullptr) return set_err(COORDX_ERR_WORKSPACE, "tcgen05 trunk: workspace too small%s (%lld < %lld)", "", (long long)ws_bytes, (long long)pl.total);
   EpiConst* epi = (EpiConst*)((uint8_t*)ws + pl.epi_off);
   const float S = 30.f * net->act_scale;
-
-  prep_epi_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], net->layer_b[L + 1], O, net->act, S, epi);
-  CX_LAUNCH_CHECK();
-  CX_CUDA(cudaMemcpyToSymbolAsync(c_epi, epi, sizeof(EpiConst), 0, cudaMemcpyDeviceToDevice, st));
 
   FwdParams fp{};
   fp.W = net->layer_w[L];
@@ -616,8 +654,42 @@ int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int
   const int64_t total = (int64_t)pl.nb * (fp.o_end - fp.o_begin);
   if (total <= 0) return 0;
   const int grid = 2 * (int)min((int64_t)(num_sms() / 2), cdiv(total, 2));
-  if (precision == COORDX_PREC_BF16) return launch_fwd_t<__nv_bfloat16>(fp, net->fusion_op, net->act, O, grid, st);
-  return launch_fwd_t<__half>(fp, net->fusion_op, net->act, O, grid, st);
+
+  prep_epi_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], net->layer_b[L + 1], O, net->act, S, epi);
+  CX_LAUNCH_CHECK();
+
+  int dev = 0;
+  CX_CUDA(cudaGetDevice(&dev));
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CX_CUDA(cudaStreamIsCapturing(st, &cap));
+  const bool eager = cap == cudaStreamCaptureStatusNone && dev >= 0 && dev < 64;
+  std::lock_guard<std::mutex> lock(g_copy_mutex);
+  const int copy = (int)(g_next_copy++ % EPI_COPIES);
+  CopyState* cs = eager ? &g_copy_state[dev][copy] : nullptr;
+  if (cs && cs->recorded && cs->last != st) CX_CUDA(cudaStreamWaitEvent(st, cs->done, 0));
+  if (g_profile) {
+    if (!g_prof_ev[0]) {
+      CX_CUDA(cudaEventCreate(&g_prof_ev[0]));
+      CX_CUDA(cudaEventCreate(&g_prof_ev[1]));
+    }
+  }
+  cudaEvent_t ev0 = g_profile ? g_prof_ev[0] : nullptr;
+  int rc;
+  switch (copy) {
+    case 0: rc = trunk_fwd_launch_copy0(fp, epi, precision, net->fusion_op, net->act, O, grid, st, ev0); break;
+    case 1: rc = trunk_fwd_launch_copy1(fp, epi, precision, net->fusion_op, net->act, O, grid, st, ev0); break;
+    case 2: rc = trunk_fwd_launch_copy2(fp, epi, precision, net->fusion_op, net->act, O, grid, st, ev0); break;
+    default: rc = trunk_fwd_launch_copy3(fp, epi, precision, net->fusion_op, net->act, O, grid, st, ev0); break;
+  }
+  CX_TRY(rc);
+  if (g_profile) CX_CUDA(cudaEventRecord(g_prof_ev[1], st));
+  if (cs) {
+    if (!cs->done) CX_CUDA(cudaEventCreateWithFlags(&cs->done, cudaEventDisableTiming));
+    CX_CUDA(cudaEventRecord(cs->done, st));
+    cs->last = st;
+    cs->recorded = true;
+  }
+  return 0;
 }
 
 bool tc_supported(const coordx_net* net, int precision) {
@@ -632,6 +704,7 @@ bool tc_supported(const coordx_net* net, int precision) {
   if (net->act != COORDX_ACT_SINE && net->act != COORDX_ACT_RELU) return false;
   return true;
 }
+#endif  // COORDX_FWD_COPY == 0
 
 }  // namespace tc
 }  // namespace coordx

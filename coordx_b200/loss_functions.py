@@ -6,6 +6,7 @@ tensor instead of the reference's six elementwise kernels (sub, pow, mean, and t
 `fused_loss(kind, out, gt)` is the tensor-level entry (`kind` 'mse' | 'bce'); CUDA fp32 tensors only - like the rest
 of the package there is no CPU path (the reference's own loss functions are plain torch and work anywhere)."""
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -33,6 +34,7 @@ class _FusedLossFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g):
         d = ctx.dout
         if d is None:

@@ -59,6 +59,24 @@ def init_weights_normal(m):
         nn.init.kaiming_normal_(m.weight, a=0.0, nonlinearity='relu', mode='fan_in')
 
 
+def init_weights_selu(m):
+    """modules.py:619-623"""
+    if type(m) in (BatchLinear, nn.Linear) and hasattr(m, 'weight'):
+        nn.init.normal_(m.weight, std=1 / math.sqrt(m.weight.size(-1)))
+
+
+def init_weights_elu(m):
+    """modules.py:626-630"""
+    if type(m) in (BatchLinear, nn.Linear) and hasattr(m, 'weight'):
+        nn.init.normal_(m.weight, std=math.sqrt(1.5505188080679277) / math.sqrt(m.weight.size(-1)))
+
+
+def init_weights_xavier(m):
+    """modules.py:633-636"""
+    if type(m) in (BatchLinear, nn.Linear) and hasattr(m, 'weight'):
+        nn.init.xavier_normal_(m.weight)
+
+
 def sine_init(m):
     """modules.py:639-644"""
     with torch.no_grad():
@@ -76,9 +94,15 @@ def first_layer_sine_init(m):
 
 
 _NONLINEARITIES = {
-    # name -> (factory, weight init, first-layer init)       (modules.py:171-177)
+    # name -> (factory, weight init, first-layer init)       (modules.py:170-176)
+    # sine / relu run on every kernel path; the others on the FP32 kernels (`precision` resolves to fp32 for them)
     'sine': (Sine, sine_init, first_layer_sine_init),
     'relu': (lambda: nn.ReLU(inplace=False), init_weights_normal, None),
+    'sigmoid': (nn.Sigmoid, init_weights_xavier, None),
+    'tanh': (nn.Tanh, init_weights_xavier, None),
+    'selu': (lambda: nn.SELU(inplace=False), init_weights_selu, None),
+    'softplus': (nn.Softplus, init_weights_normal, None),
+    'elu': (lambda: nn.ELU(inplace=False), init_weights_elu, None),
 }
 
 
@@ -117,7 +141,7 @@ class _NetDesc:
         n.n_layers = len(layers)
         for k, (o, i) in enumerate(layers):
             n.layer_in[k], n.layer_out[k] = i, o
-        n.act = _lib.ACT_SINE if block.nonlinearity == 'sine' else _lib.ACT_RELU
+        n.act = _lib.ACTS[block.nonlinearity]
         n.fusion_op = {'sum': _lib.FUSE_SUM, 'prod': _lib.FUSE_PROD}[block.fusion_operator]
         n.fusion_before_act = int(block.fusion_before_act)
         n.has_code = int(block.learn_code)
@@ -170,19 +194,44 @@ def _grads_for(block, params):
 
 
 _WS = {}
+_WS_KEEP_BYTES = int(float(os.environ.get('COORDX_WS_KEEP_MB', '1024')) * (1 << 20))
 
 
 def _workspace(nbytes, device):
-    """Grow-only scratch buffer per (device, stream): kernels that use it are ordered on that stream,
-    so consecutive calls may share it (the C library never keeps pointers into it across calls)."""
+    """Scratch buffer for one C call.  Buffers up to COORDX_WS_KEEP_MB (default 1 GiB) are cached per (device, stream)
+    and grow on demand: kernels that use them are ordered on that stream, so consecutive calls may share one (the C
+    library never keeps pointers into it across calls).  Larger requests (the stored dZ tiles of a big training
+    grid: 2 GB for 2048^2, 8 GB for 4096^2) are plain allocations that go back to torch's caching allocator when the
+    call returns, so `torch.cuda.empty_cache()` can hand the memory back to the driver."""
     nbytes = max(int(nbytes), 256)
+    if nbytes > _WS_KEEP_BYTES or torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _WS.get(key)
-    if ws is None or ws.numel() < nbytes or torch.cuda.is_current_stream_capturing():
+    if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        if not torch.cuda.is_current_stream_capturing():
-            _WS[key] = ws
+        _WS[key] = ws
     return ws
+
+
+def release_workspaces():
+    """Drop every cached scratch buffer (they are re-created on demand)."""
+    _WS.clear()
+
+
+def _backward_workspace(lib, net, n_arr, n0, prec, device):
+    """Workspace of coordx_trunk_backward: the preferred size (the tcgen05 path keeps its dZ tiles between its two
+    passes), or - when that allocation fails - the minimal one, with which the library recomputes instead."""
+    want = lib.coordx_trunk_workspace_bytes(net, n_arr, 0, n0, prec, 1)
+    try:
+        return _workspace(want, device)
+    except torch.cuda.OutOfMemoryError:
+        small = lib.coordx_trunk_workspace_bytes(net, n_arr, 0, n0, prec, 2)
+        if small >= want:
+            raise
+        release_workspaces()
+        torch.cuda.empty_cache()
+        return _workspace(small, device)
 
 
 def _net_desc(block, params, n_tables=None):
@@ -312,8 +361,7 @@ class _FusionFn(torch.autograd.Function):
         f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
         df_arr = _lib.ptr_array([f.data_ptr() for f in dfeats])
         with torch.cuda.device(dev):
-            ws_bytes = lib.coordx_trunk_workspace_bytes(desc.net, n_arr, 0, ns[0], ctx.prec, 1)
-            ws = _workspace(ws_bytes, dev)
+            ws = _backward_workspace(lib, desc.net, n_arr, ns[0], ctx.prec, dev)
             _lib.check(lib.coordx_trunk_backward(desc.net, f_arr, n_arr, 0, ns[0], d.data_ptr(), grads, df_arr, ctx.prec,
                                                  ws.data_ptr(), ws.numel(), _stream_ptr()), 'coordx_trunk_backward')
         used = block.trunk_param_mask()

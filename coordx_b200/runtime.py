@@ -167,12 +167,13 @@ class CapturedTrainStep:
 
     def __init__(self, model: 'M.SingleBVPNet', coords: Sequence[torch.Tensor], gt: torch.Tensor, loss='mse',
                  lr: float = 1e-4, clip_grad: bool = False, optimizer: torch.optim.Optimizer = None, warmup: int = 3,
-                 lr_gamma: float = None, world: int = 1, group=None):
+                 lr_gamma: float = None, world: int = 1, group=None, grad_weight: float = None):
         self.model = model
         # world > 1: the grid is sharded along axis 0 (sharding.py) and `coords` / `gt` are this rank's slab; the one
         # exchange of the step - the flat all-reduce of the weight gradients - is captured in the graph with the rest
         # (NCCL collectives are capturable), so a multi-GPU step is still ONE graph launch per rank
-        self.world, self.group = int(world), group
+        # grad_weight: this rank's share of the grid points (sharding.slab_weight) when the slabs are not equally long
+        self.world, self.group, self.grad_weight = int(world), group, grad_weight
         self.static_coords = [c.detach().clone() for c in coords]
         self.static_gt = gt.detach().clone()
         self.clip_grad = clip_grad
@@ -236,7 +237,7 @@ class CapturedTrainStep:
         loss.backward()
         if self.world > 1:
             from . import sharding
-            sharding.allreduce_grads(self.params, self.world, group=self.group)
+            sharding.allreduce_grads(self.params, self.world, group=self.group, weight=self.grad_weight)
         if self.clip_grad and not self._own_opt:                 # (DeviceAdam clips inside its step)
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=1.)
         self.opt.step()

@@ -40,17 +40,24 @@ def shard_target(gt: torch.Tensor, shape: Sequence[int], rank: int, world: int) 
     return gt[:, a * inner:b * inner]
 
 
-def allreduce_grads(params: Iterable[torch.nn.Parameter], world: int, average: bool = True, group=None) -> None:
-    """One flat all-reduce of every parameter gradient.  With `average` the per-rank losses are means over
-    equally sized slabs, so the mean of the gradients is the gradient of the global mean loss."""
+def allreduce_grads(params: Iterable[torch.nn.Parameter], world: int, average: bool = True, group=None,
+                    weight: float | None = None) -> None:
+    """One flat all-reduce of every parameter gradient.
+
+    average=True, weight=None: plain mean over ranks - the gradient of the global mean loss when every rank's loss is
+    a mean over an EQUALLY sized slab.  When the slabs differ (n0 % world != 0, `slab_range` hands out unequal
+    slabs), pass `weight` = this rank's share of the points (`slab_weight`): the per-rank mean-loss gradients are
+    then combined as sum_r weight_r * grad_r, which is the global-mean gradient for any split."""
     if world <= 1:
         return
     ps = [p for p in params if p.grad is not None]
     if not ps:
         return
     flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    if weight is not None:
+        flat *= float(weight)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
+    if average and weight is None:
         flat /= world
     off = 0
     for p in ps:
@@ -59,10 +66,27 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], world: int, average: b
         off += n
 
 
+def slab_weight(n0: int, rank: int, world: int) -> float:
+    """This rank's share of the grid points (its slab's rows over all rows): the `weight` of `allreduce_grads`."""
+    a, b = slab_range(n0, rank, world)
+    return (b - a) / float(n0) if n0 > 0 else 0.0
+
+
 def gather_output(out_slab: torch.Tensor, world: int, group=None) -> torch.Tensor:
-    """Optional: assemble the full [B, P, O] output from equal-size slabs (inference can also stay sharded)."""
+    """Optional: assemble the full [B, P, O] output from the ranks' slabs (inference can also stay sharded).
+    Slabs may differ in length along dim 1 (n0 % world != 0): sizes are exchanged first and the slabs padded to the
+    longest for the all_gather."""
     if world <= 1:
         return out_slab
+    out_slab = out_slab.contiguous()
+    mine = torch.tensor([out_slab.shape[1]], dtype=torch.int64, device=out_slab.device)
+    sizes = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(sizes, mine, group=group)
+    sizes = [int(t.item()) for t in sizes]
+    longest = max(sizes)
+    if out_slab.shape[1] < longest:
+        pad = out_slab.new_zeros(out_slab.shape[0], longest - out_slab.shape[1], *out_slab.shape[2:])
+        out_slab = torch.cat([out_slab, pad], dim=1)
     parts = [torch.empty_like(out_slab) for _ in range(world)]
-    dist.all_gather(parts, out_slab.contiguous(), group=group)
-    return torch.cat(parts, dim=1)
+    dist.all_gather(parts, out_slab, group=group)
+    return torch.cat([p[:, :k] for p, k in zip(parts, sizes)], dim=1)

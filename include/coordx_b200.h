@@ -37,7 +37,9 @@ extern "C" {
 #define COORDX_MAX_BRANCHES 4
 #define COORDX_MAX_LAYERS 12
 
-enum { COORDX_ACT_SINE = 0, COORDX_ACT_RELU = 1 };
+/* sine and relu run on every path; the rest of the reference's table (modules.py:170-176) on the FP32 path */
+enum { COORDX_ACT_SINE = 0, COORDX_ACT_RELU = 1, COORDX_ACT_SIGMOID = 2, COORDX_ACT_TANH = 3, COORDX_ACT_SELU = 4,
+       COORDX_ACT_SOFTPLUS = 5, COORDX_ACT_ELU = 6 };
 enum { COORDX_FUSE_SUM = 0, COORDX_FUSE_PROD = 1 };
 enum { COORDX_LOSS_MSE = 0, COORDX_LOSS_BCE = 1 };
 /* arithmetic of the post-fusion trunk GEMM */
@@ -122,8 +124,12 @@ int coordx_branch_backward_saved(const coordx_net* net, int branch, const float*
 /* ---- fusion + trunk: SplitFCBlock.forward_fusion, modules.py:329-354 -----------------
  * feats[c] [n[c], fuse_width]  ->  out [(row_end-row_begin) * prod_{c>0} n[c], out_width]
  * The broadcast [N_0,..,N_{C-1},F] tensor of modules.py:336-341 is never materialised for
- * the whole grid: fp32 builds it in bounded chunks of whole axis-0 rows inside `ws`; the
- * tcgen05 path builds 128-point tiles in shared memory.                                  */
+ * the whole grid: fp32 builds it in bounded chunks (whole axis-0 rows, or pieces of one
+ * row when a row alone is too long) inside `ws`; the tcgen05 path builds 128-point tiles
+ * in shared memory.
+ * backward: 0 = forward, 1 = backward (preferred size: the tcgen05 path keeps its 16-bit
+ * dZ tiles, 64 KB per 128 points, between its two passes), 2 = backward, minimal size
+ * (the tcgen05 path then recomputes instead); coordx_trunk_backward takes either.       */
 size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t row_begin,
                                     int64_t row_end, int precision, int backward);
 int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const int64_t* n,

@@ -84,6 +84,12 @@ CASES = [
     # sum-fused sine nets with three axes / a 2-D axis and RGB output (the separable trunk path)
     ('occ_sine_sum_h64', dict(type='sine', in_features=3, out_features=1, hidden_features=64, fusion_operator='sum'), (9, 10, 11), 'bce', 'rand'),
     ('video_st_sine_sum_h256', dict(type='sine', in_features=3, out_features=3, hidden_features=256, split_rule=[1, 2], fusion_operator='sum'), (12, 150), 'mse', 'rand'),
+    # the rest of the nonlinearity table (modules.py:170-176; --model_type tanh / selu / ...)
+    ('img_tanh_prod_h64', dict(type='tanh', out_features=1, hidden_features=64, fusion_operator='prod'), (14, 19), 'mse', 'linspace'),
+    ('img_sigmoid_sum_h64', dict(type='sigmoid', out_features=1, hidden_features=64, fusion_operator='sum'), (11, 23), 'mse', 'rand'),
+    ('img_selu_prod_h64', dict(type='selu', out_features=1, hidden_features=64, fusion_operator='prod'), (13, 16), 'mse', 'rand'),
+    ('occ_elu_sum_h64', dict(type='elu', in_features=3, out_features=1, hidden_features=64, fusion_operator='sum'), (5, 6, 9), 'bce', 'rand'),
+    ('img_softplus_prod_h64', dict(type='softplus', out_features=1, hidden_features=64, fusion_operator='prod'), (12, 15), 'mse', 'linspace'),
 ]
 
 

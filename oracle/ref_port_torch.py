@@ -39,7 +39,12 @@ def _linear(x, W, b, num_input):
 def _act(cfg: SplitCfg, x):
     if cfg.nonlinearity == 'sine':
         return torch.sin(30 * cfg.act_scale * x)
-    return torch.relu(x)
+    nl = cfg.nonlinearity
+    if nl == 'relu':
+        return torch.relu(x)
+    fn = {'sigmoid': torch.sigmoid, 'tanh': torch.tanh, 'selu': torch.nn.functional.selu,
+          'softplus': torch.nn.functional.softplus, 'elu': torch.nn.functional.elu}     # modules.py:170-176
+    return fn[nl](x)
 
 
 def _has_act(cfg, k):

@@ -7,5 +7,5 @@ cd "$(dirname "$0")/.."
 B=coordx_b200/_build
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr \
   "$@" -c -o $B/trunk_bwd_tc2_$TAG.o coordx_b200/csrc/trunk_bwd_tc2.cu
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $B/libcoordx_$TAG.so $B/coordx_abi.o $B/trunk_fwd_tc.o $B/trunk_bwd_tc.o $B/trunk_bwd_tc2_$TAG.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $B/libcoordx_$TAG.so $B/coordx_abi.o $B/trunk_fwd_tc.o $B/trunk_fwd_tc_copy1.o $B/trunk_fwd_tc_copy2.o $B/trunk_fwd_tc_copy3.o $B/trunk_bwd_tc.o $B/trunk_bwd_tc2_$TAG.o
 echo built $B/libcoordx_$TAG.so

@@ -35,13 +35,13 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, H=10):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         cfg = O.SplitCfg(in_features=2, coord_dim=2, out_features=1, hidden_features=32, fusion_operator='prod')
         p = O.init_params(cfg, np.random.default_rng(0), dtype=np.float64)
-        H, W = 10, 6                                   # 10 rows over 2 ranks: 5 + 5
+        W = 6                                          # H = 10 rows over 2 ranks: 5 + 5; H = 9: 5 + 4
         xs = torch.linspace(-1, 1, H, dtype=torch.float64).reshape(1, H, 1, 1)
         ys = torch.linspace(-1, 1, W, dtype=torch.float64).reshape(1, 1, W, 1)
         gt = torch.as_tensor(np.random.default_rng(1).uniform(-1, 1, (1, H * W, 1)))
@@ -50,14 +50,17 @@ def _worker(rank, world, port, q):
         coords = [c.reshape(-1, 1).numpy() for c in mine]
         cache = {}
         out, _ = O.forward_grid(p, cfg, coords, cache)
-        loss, dout = O.image_mse(out, gt_mine[0].numpy())     # mean over this rank's (equal-size) slab
+        loss, dout = O.image_mse(out, gt_mine[0].numpy())     # mean over this rank's slab
         grads, _ = O.backward_grid(p, cfg, cache, dout)
         params = []
         for k in sorted(grads):
             t = torch.nn.Parameter(torch.as_tensor(p[k].copy()))
             t.grad = torch.as_tensor(np.ascontiguousarray(grads[k]))
             params.append(t)
-        sharding.allreduce_grads(params, world, average=True)
+        if H % world == 0:
+            sharding.allreduce_grads(params, world, average=True)          # equal slabs: plain mean
+        else:
+            sharding.allreduce_grads(params, world, weight=sharding.slab_weight(H, rank, world))
         full = sharding.gather_output(torch.as_tensor(out)[None], world)
         if rank == 0:
             # single-process truth on the whole grid
@@ -76,11 +79,13 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_gloo_grad_allreduce_equals_full_grid():
+@pytest.mark.parametrize('H', [10, 9])
+def test_two_rank_gloo_grad_allreduce_equals_full_grid(H):
+    """H = 9: unequal slabs (5 + 4 rows) - gradients weighted by the slab's share, outputs gathered with padding."""
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, H)) for r in range(2)]
     for pr in procs:
         pr.start()
     status, gerr, oerr = q.get(timeout=180)
