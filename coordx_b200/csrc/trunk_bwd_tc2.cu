@@ -38,18 +38,9 @@ constexpr uint32_t D2_DOUT = D2_BAR + 256;                 // dout staging: D st
 constexpr int DW2_THREADS = 28 * 32;
 // tuning knobs (A/B builds: scripts/build_variant_bwd2.sh)
 #ifndef COORDX_DW2_NPOLY
-#define COORDX_DW2_NPOLY 4          // of the 8 (even, odd) pairs of a thread's 16 values, how many take the FMA-pipe polynomial
+#define COORDX_DW2_NPOLY 2          // of the 8 (even, odd) pairs of a thread's 16 values, how many take the FMA-pipe polynomial
 #endif
-#ifndef COORDX_DW2_ELECT_ARRIVE
-#define COORDX_DW2_ELECT_ARRIVE 1   // one mbarrier arrive per E1 warp (after __syncwarp) instead of one per thread
-#endif
-#ifndef COORDX_DW2_SCALAR_POLY
-#define COORDX_DW2_SCALAR_POLY 0    // polynomial half in scalar FFMAs with immediate coefficients instead of packed fp32x2
-#endif
-#ifndef COORDX_DW2_SKEW
-#define COORDX_DW2_SKEW 0           // SM clocks by which the E1 warps of point groups 2, 3 start late (two early + two late warps per scheduler)
-#endif
-constexpr int D2_E1_ARRIVALS = COORDX_DW2_ELECT_ARRIVE ? 16 : 512;
+constexpr int D2_E1_ARRIVALS = 16;      // one elected arrive per E1 warp
 __host__ __device__ constexpr bool d2_poly_pair(int e2) {
   return (e2 * COORDX_DW2_NPOLY) / 8 != ((e2 + 1) * COORDX_DW2_NPOLY) / 8;
 }
@@ -72,7 +63,10 @@ struct Bars2 {
 // sin(2 pi r) and cos(2 pi r) on r in [-1/2, 1/2] (r = fractional part of the angle in revolutions), two values per
 // packed fp32x2 instruction.  Minimax fits: max error 2.5e-4 (sin, feeds only the dWf sums) and 4.0e-5 (cos, feeds dZ,
 // which is rounded to 16 bits right after).  E1 evaluates HALF of its elements this way and half on the MUFU unit:
-// sin AND cos of every element on the MUFU (16 results / clk / SM) was the floor of the whole pass.
+// sin AND cos of every element on the MUFU (16 results / clk / SM) was the floor of the whole pass.  The share is
+// COORDX_DW2_NPOLY of every 8 pairs: scripts/micro/micro_e1.cu times this arithmetic alone (profiles/r02b_micro_e1.txt:
+// 1062 clk per 16 values x 4 warps with 0 / 8, 870 with 2 / 8, 919 with 4 / 8, 1181 with 8 / 8 - MUFU-bound below 2,
+// issue-bound above; scalar FFMAs with immediate coefficients instead of the packed ones are 10 % slower).
 __device__ __forceinline__ uint64_t f2x(float v) { return ptx::pack_f32x2(v, v); }
 __device__ __forceinline__ void sincos_rev_x2(uint64_t t2, uint64_t& sn, uint64_t& cs) {
   const uint64_t m2 = ptx::add_f32x2(t2, f2x(12582912.f));            // 1.5 * 2^23: rounds t to the nearest integer
@@ -88,22 +82,6 @@ __device__ __forceinline__ void sincos_rev_x2(uint64_t t2, uint64_t& sn, uint64_
   pc = ptx::fma_f32x2(pc, q2, f2x(-19.731046676635742f));
   cs = ptx::fma_f32x2(pc, q2, f2x(0.9999598264694214f));
 }
-// the same polynomials, one value at a time: the coefficients are immediates of the FFMAs
-__device__ __forceinline__ void sincos_rev(float t, float& sn, float& cs) {
-  const float m = t + 12582912.f;
-  const float n = m - 12582912.f;
-  const float r = t - n;
-  const float q = r * r;
-  float ps = fmaf(q, -56.08980178833008f, 77.93164825439453f);
-  ps = fmaf(ps, q, -41.093868255615234f);
-  ps = fmaf(ps, q, 6.27863883972168f);
-  sn = ps * r;
-  float pc = fmaf(q, 45.64854431152344f, -82.40443420410156f);
-  pc = fmaf(pc, q, 64.67355346679688f);
-  pc = fmaf(pc, q, -19.731046676635742f);
-  cs = fmaf(pc, q, 0.9999598264694214f);
-}
-
 template <typename T, int OP, int ACT, int O>
 __global__ void __launch_bounds__(DW2_THREADS, 1)
 trunk_bwd_dw2_kernel(const BwdParams p) {
@@ -359,10 +337,6 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
     int dsg = 0, dsuse = 0;
     const bool tr = q == 0 && lane == 0 && (pq == 0 || pq == 3);
     const int trole = pq == 0 ? 1 : 2;
-    if (COORDX_DW2_SKEW > 0 && pq >= 2) {          // out of phase with the other two warps of this scheduler
-      const long long t_go = clock64() + COORDX_DW2_SKEW;
-      while (clock64() < t_go) {}
-    }
     for (int s = 0; s < n_sub; ++s) {
       const int hh = s & 1;
       const uint32_t zb = s & 1;
@@ -390,16 +364,7 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
           const uint64_t zz = ptx::pack_f32x2(__uint_as_float(r[2 * e2]), __uint_as_float(r[2 * e2 + 1]));
           uint64_t sn, cs;
           if (d2_poly_pair(e2)) {                  // polynomial share
-            if (COORDX_DW2_SCALAR_POLY) {
-              float t0, t1, s0, s1, c0, c1;
-              ptx::unpack_f32x2(ptx::fma_f32x2(zz, S2r, B2r), t0, t1);
-              sincos_rev(t0, s0, c0);
-              sincos_rev(t1, s1, c1);
-              sn = ptx::pack_f32x2(s0, s1);
-              cs = ptx::pack_f32x2(c0, c1);
-            } else {
-              sincos_rev_x2(ptx::fma_f32x2(zz, S2r, B2r), sn, cs);
-            }
+            sincos_rev_x2(ptx::fma_f32x2(zz, S2r, B2r), sn, cs);
           } else {                                 // MUFU half
             float th0, th1;
             ptx::unpack_f32x2(ptx::fma_f32x2(zz, S2, B2), th0, th1);
@@ -445,12 +410,8 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
       }
       if (tr) trace_stamp(p, trole, s, 2);
       if (hh == 1) {                               // last read of this tile's staged dout
-        if (COORDX_DW2_ELECT_ARRIVE) {
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(B.dsempty + 8 * dsg);
-        } else {
-          ptx::mbar_arrive(B.dsempty + 8 * dsg);
-        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(B.dsempty + 8 * dsg);
         if (++dsg == DST) { dsg = 0; ++dsuse; }
       }
       // dZ^T goes back into TENSOR MEMORY, over the first 8 of this warp's own 16 Z^T columns (all of them are in
@@ -468,12 +429,8 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      if (COORDX_DW2_ELECT_ARRIVE) {
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(B.dzfull + 8 * zb);
-      } else {
-        ptx::mbar_arrive(B.dzfull + 8 * zb);
-      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(B.dzfull + 8 * zb);
       if (tr) trace_stamp(p, trole, s, 3);
     }
     if (my_tiles > 0) {

@@ -69,6 +69,18 @@ constexpr int NUM_THREADS = 20 * 32;
 #ifndef COORDX_FWD_MUFU_COLS
 #define COORDX_FWD_MUFU_COLS 32
 #endif
+// of the 16 column pairs of a 32-column batch, how many evaluate sin on the FMA pipe (packed fp32x2 minimax polynomial,
+// max error 2.5e-4) instead of the MUFU: the epilogue is MUFU-bound (one sin per 512 tensor FLOPs = the tcgen05 time of
+// the tile) with issue slots to spare
+#ifndef COORDX_FWD_POLY_PAIRS
+#define COORDX_FWD_POLY_PAIRS 4
+#endif
+#ifndef COORDX_FWD_EPI0_BATCHES
+#define COORDX_FWD_EPI0_BATCHES 3
+#endif
+__host__ __device__ constexpr bool fwd_poly_pair(int pr) {
+  return (pr * COORDX_FWD_POLY_PAIRS) / 16 != ((pr + 1) * COORDX_FWD_POLY_PAIRS) / 16;
+}
 // launch: 640 threads x 96 registers; then 256 x 96 (epilogue, unchanged) + 256 x 128 (producers) + 128 x 32 (MMA warpgroup) = 640 x 96
 constexpr int REGS_PROD = 128, REGS_MMA = 32;
 
@@ -76,6 +88,7 @@ constexpr int REGS_PROD = 128, REGS_MMA = 32;
 // unrolling => FFMA operands straight from the constant bank
 struct EpiConst {
   float bias[HD];            // sine: S*b ; relu: b
+  float bias_rev[HD];        // sine: S*b / 2 pi (angle in revolutions, for the columns that take the polynomial)
   float wf[MAX_O][HD];       // final layer weight
   float bf[MAX_O];
 };
@@ -110,6 +123,7 @@ __constant__ EpiConst c_epi;     // this copy's image of the epilogue constants
 //   acc  += sin * wf                      FHFMA (fp16 x fp16 + fp32)
 // Error of this path: 6.5e-4 rms / 2.2e-3 max per activation (oracle-checked in tests), below the
 // ~1.3e-3 rad the bf16 operands already put on the sine's argument; output parity stays well inside 2e-3.
+__device__ __forceinline__ uint64_t f2x(float v) { return ptx::pack_f32x2(v, v); }
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
 __device__ __forceinline__ float fhfma_lo(uint32_t a, uint32_t b, float c) {      // c + a.lo * b.lo
@@ -354,6 +368,8 @@ trunk_fwd_tc_kernel(const FwdParams p) {
     //  direct constant-bank operands)
     auto run = [&](auto EC) {
     constexpr int E = decltype(EC)::value;
+    // group 0 also finalises and stores every tile: it takes fewer of the eight 32-column batches
+    constexpr int NB = E == 0 ? COORDX_FWD_EPI0_BATCHES : 8 - COORDX_FWD_EPI0_BATCHES, CB0 = E == 0 ? 0 : COORDX_FWD_EPI0_BATCHES;
     int64_t t_cur = c_begin + rank;
     const int n_o32 = (int)n_o;
     int jb_e = (int)(t_cur / n_o), ol_e = (int)(t_cur - (int64_t)jb_e * n_o);
@@ -385,7 +401,7 @@ trunk_fwd_tc_kernel(const FwdParams p) {
       ptx::tc_fence_after();
       const bool valid = t_cur < c_end;
       const int64_t jb = jb_e, o_local = ol_e;     // tile -> (inner block, outer index), advanced without divisions
-      const uint32_t taddr = tmem_base + a * HD + E * (HD / 2) + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + a * HD + CB0 * 32 + ((uint32_t)(q * 32) << 16);
       // acc2: packed pair (even-column sum, odd-column sum) fed by FFMA2; acc: the polynomial path's FHFMAs
       uint64_t acc2[O];
       float acc[O];
@@ -396,7 +412,7 @@ trunk_fwd_tc_kernel(const FwdParams p) {
       // weights are direct constant-bank operands of the FFMAs (an LDC per value is far slower).
       uint32_t ra[32], rb[32];
       auto consume = [&](const uint32_t (&r)[32], int cbl) {
-        const int cb = E * 4 + cbl;               // 32-column batch inside the 256-wide accumulator
+        const int cb = CB0 + cbl;                 // 32-column batch inside the 256-wide accumulator
         constexpr int NMU = ACT == COORDX_ACT_SINE ? NM : 32;
 #pragma unroll
         for (int i = 0; i < NMU; i += 2) {
@@ -404,17 +420,31 @@ trunk_fwd_tc_kernel(const FwdParams p) {
           // 2 x (FMUL.RZ + MUFU.SIN), FFMA2 into the packed accumulator = 3.25 issue slots per activation
           const int k = cb * 32 + i;
           const uint64_t zz = ptx::pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-          float t0, t1;
-          ptx::unpack_f32x2(ptx::add_f32x2(zz, ptx::pack_f32x2(c_epi.bias[k], c_epi.bias[k + 1])), t0, t1);
-          float h0, h1;
-          if (ACT == COORDX_ACT_SINE) {
-            h0 = __sinf(t0);
-            h1 = __sinf(t1);
+          uint64_t hh;
+          if (ACT == COORDX_ACT_SINE && fwd_poly_pair(i >> 1)) {
+            // sin(2 pi t), t = (S z + S b) / 2 pi: r = t - rint(t) in [-1/2, 1/2] by the 1.5 * 2^23 trick, odd polynomial in r
+            const uint64_t t2 = ptx::fma_f32x2(zz, f2x(0.15915494309189535f), ptx::pack_f32x2(c_epi.bias_rev[k], c_epi.bias_rev[k + 1]));
+            const uint64_t m2 = ptx::add_f32x2(t2, f2x(12582912.f));
+            const uint64_t n2 = ptx::add_f32x2(m2, f2x(-12582912.f));
+            const uint64_t rr = ptx::fma_f32x2(n2, f2x(-1.f), t2);
+            const uint64_t q2 = ptx::mul_f32x2(rr, rr);
+            uint64_t ps = ptx::fma_f32x2(q2, f2x(-56.08980178833008f), f2x(77.93164825439453f));
+            ps = ptx::fma_f32x2(ps, q2, f2x(-41.093868255615234f));
+            ps = ptx::fma_f32x2(ps, q2, f2x(6.27863883972168f));
+            hh = ptx::mul_f32x2(ps, rr);
           } else {
-            h0 = fmaxf(t0, 0.f);
-            h1 = fmaxf(t1, 0.f);
+            float t0, t1;
+            ptx::unpack_f32x2(ptx::add_f32x2(zz, ptx::pack_f32x2(c_epi.bias[k], c_epi.bias[k + 1])), t0, t1);
+            float h0, h1;
+            if (ACT == COORDX_ACT_SINE) {
+              h0 = __sinf(t0);
+              h1 = __sinf(t1);
+            } else {
+              h0 = fmaxf(t0, 0.f);
+              h1 = fmaxf(t1, 0.f);
+            }
+            hh = ptx::pack_f32x2(h0, h1);
           }
-          const uint64_t hh = ptx::pack_f32x2(h0, h1);
 #pragma unroll
           for (int oo = 0; oo < O; ++oo)
             acc2[oo] = ptx::fma_f32x2(hh, ptx::pack_f32x2(c_epi.wf[oo][k], c_epi.wf[oo][k + 1]), acc2[oo]);
@@ -455,21 +485,20 @@ trunk_fwd_tc_kernel(const FwdParams p) {
       };
       ptx::tmem_ld_32x32b_x32(taddr, ra);
 #pragma unroll
-      for (int cb = 0; cb < HD / 64; cb += 2) {
+      for (int b = 0; b < NB; ++b) {
         ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32b_x32(taddr + (cb + 1) * 32, rb);
-        consume(ra, cb);
-        ptx::tmem_ld_wait();
-        if (cb + 2 < HD / 64) {
-          ptx::tmem_ld_32x32b_x32(taddr + (cb + 2) * 32, ra);
+        if (b + 1 < NB) {
+          if (b & 1) ptx::tmem_ld_32x32b_x32(taddr + (b + 1) * 32, ra);
+          else ptx::tmem_ld_32x32b_x32(taddr + (b + 1) * 32, rb);
         } else {
-          // the last column batch is in registers: hand the accumulator back to the tensor core now, a quarter of
+          // the last column batch is in registers: hand the accumulator back to the tensor core now, one batch of
           // the tile's epilogue work early
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(tempty_remote);
         }
-        consume(rb, cb + 1);
+        if (b & 1) consume(rb, b);
+        else consume(ra, b);
       }
       if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 2);
 #pragma unroll
@@ -576,7 +605,10 @@ static __global__ void __launch_bounds__(256)
 prep_epi_kernel(const float* __restrict__ b, const float* __restrict__ Wf, const float* __restrict__ bf, int O, int act,
                 float S, EpiConst* __restrict__ epi) {
   const int idx = blockIdx.x * 256 + threadIdx.x;          // over MAX_O * 256
-  if (idx < HD) epi->bias[idx] = act == COORDX_ACT_SINE ? S * b[idx] : b[idx];
+  if (idx < HD) {
+    epi->bias[idx] = act == COORDX_ACT_SINE ? S * b[idx] : b[idx];
+    epi->bias_rev[idx] = act == COORDX_ACT_SINE ? S * b[idx] * 0.15915494309189535f : 0.f;
+  }
   if (idx < MAX_O * HD) {
     const int o = idx >> 8;
     epi->wf[o][idx & 255] = o < O ? Wf[idx] : 0.f;
