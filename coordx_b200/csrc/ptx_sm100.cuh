@@ -58,6 +58,39 @@ __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async
 template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- hand-over of bulk-stored global data to another CTA of the same grid through a counter in global memory.
+// Writer: cp.async.bulk.wait_group (not .read) returns when the group's writes have been performed - they sit in the
+// L2, the point of coherence of every SM - then one relaxed gpu-scope reduction on the counter.  Reader: relaxed
+// gpu-scope loads of the counter (L1 bypassed), then its own bulk loads, which read the L2 through the copy engine.
+// The formally complete version (proxy fence + fence.acq_rel.gpu + red.release / ld.acquire, COORDX_PUBLISH_RELEASE=1)
+// costs two MEMBAR.GPU per store on the writer and an L1 invalidation per poll on the reader; the data path here never
+// touches an L1 (bulk store out of shared memory, bulk load into shared memory), which is what those fences guard.
+#ifndef COORDX_PUBLISH_RELEASE
+#define COORDX_PUBLISH_RELEASE 0
+#endif
+__device__ __forceinline__ void fence_proxy_async_all() {
+#if COORDX_PUBLISH_RELEASE
+  asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void publish_add(uint32_t* flag) {
+#if COORDX_PUBLISH_RELEASE
+  asm volatile("fence.proxy.async;\n\tfence.acq_rel.gpu;\n\tred.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+#else
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+#if COORDX_PUBLISH_RELEASE
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#else
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
+  return v;
+}
 
 __device__ __forceinline__ void prefetch_l1(const void* gptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(gptr)); }
 

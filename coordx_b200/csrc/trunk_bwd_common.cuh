@@ -57,6 +57,10 @@ struct BwdParams {
   float* db;                 // [256] +=
   float* dWf;                // [O, 256] +=
   float S;
+  uint32_t* flags;           // fused kernel: [tiles] stores completed per tile (4 = both halves x both sub-tiles), zeroed by the host
+  int fused_pairs;           // fused kernel: number of dW CTA pairs (the other CTAs of the grid run the feature-gradient pass)
+  int fused_chunk;           // fused kernel: tiles per hand-over chunk
+  int fused_groups;          // fused kernel: groups of CTAs that sweep a range of tiles together
 };
 
 // consts[] layout (floats): [256] bias' | [MAX_O][256] wfs | loss scale, 1 / loss scale, max|dout| bits, pad
@@ -92,6 +96,7 @@ __device__ __forceinline__ void load_rowvec8(const BwdParams& p, int64_t o, int 
 // ---- entry points of trunk_bwd_tc2.cu
 int launch_dw2(const BwdParams& bp, int precision, int op, int act, int O, int grid, cudaStream_t st);
 int launch_dfeat(const BwdParams& bp, int precision, int op, int n_cta, cudaStream_t st);
+int launch_bwd_fused(const BwdParams& bp, int precision, int op, int act, int O, int grid, cudaStream_t st);
 
 }  // namespace tcb
 }  // namespace coordx

@@ -1432,8 +1432,23 @@ static bool bwd_recompute_forced() {
 static long long* g_bwd_trace = nullptr;
 static int g_bwd_trace_pass = 1;      // 0 = dW pass, 1 = dH pass A, 2 = dH pass B
 
+// COORDX_BWD_FUSED=1: both passes of the stored-dZ path in ONE launch (trunk_bwd_fused_kernel) when the grid has at
+// least FUSED_MIN_TILES_PER_SM tiles per SM.  Opt-in: measured on 2048^2 (profiles/r02f_fused_bwd_sweep.txt) the dW
+// CTAs keep their stand-alone rate (2.28 us per tile and pair) but a feature-gradient CTA needs 1.9-2.1 us per tile next
+// to them - no faster than HBM-fed - so the best split (1.45 ms) does not beat the two launches (1.01 + 0.43 ms).
+// COORDX_BWD_FUSED_PAIRS / _CHUNK / _GROUPS override the role split (default: 3/8 of the SMs as dW pairs), the
+// hand-over chunk and the number of CTA groups; a negative chunk makes the consumers idle (producer-only timing).
+constexpr int FUSED_MIN_TILES_PER_SM = 16;
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? atoi(e) : dflt;
+}
+static bool bwd_fused_wanted(int64_t tiles) {
+  return env_int("COORDX_BWD_FUSED", 0) != 0 && tiles >= (int64_t)FUSED_MIN_TILES_PER_SM * num_sms() && num_sms() >= 8;
+}
+
 struct BwdPlan {
-  size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, rows_off, dz_off, total;
+  size_t w_img_off, epi_off, consts_off, innerA_off, innerB_off, drv_off, rows_off, flags_off, dz_off, total;
   bool reuse;
   int nbA, nbB;
   int64_t n_innerA, n_innerB, n_oA;
@@ -1456,6 +1471,7 @@ static BwdPlan plan_bwd(const coordx_net* net, const int64_t* n, int64_t r0, int
   pl.drv_off = off; off += C == 3 ? align_up((size_t)pl.n_oA * HD * 4, 1024) : 0;
   pl.rows_off = off; off += align_up((size_t)max(pl.n_innerA, pl.n_oA) * HD * 2, 1024);   // 16-bit rowvec rows (din pass / pass B)
   pl.reuse = reuse;
+  pl.flags_off = off; off += reuse ? align_up((size_t)pl.nbA * pl.n_oA * 4, 1024) : 0;    // per-tile hand-over counters (fused kernel)
   pl.dz_off = off; off += pl.reuse ? (size_t)pl.nbA * pl.n_oA * (4 * CH) : 0;
   pl.total = off;
   return pl;
@@ -1525,6 +1541,30 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
                                                                                 net->fusion_op, base + pl.rows_off);
       CX_LAUNCH_CHECK();
       a.outer_img = base + pl.rows_off;
+      if (pl.reuse && bwd_fused_wanted(total)) {
+        // ---------------- dW pass and feature-gradient pass side by side in one launch
+        const int sms = num_sms();
+        int pairs = env_int("COORDX_BWD_FUSED_PAIRS", (sms * 3 + 4) / 8);
+        pairs = max(1, min(pairs, (sms - 1) / 2));
+        a.flags = (uint32_t*)(base + pl.flags_off);
+        a.fused_pairs = pairs;
+        a.fused_chunk = env_int("COORDX_BWD_FUSED_CHUNK", 4);
+        if (a.fused_chunk == 0) a.fused_chunk = 1;
+        const int cons = sms - 2 * pairs;          // every group needs a pair and a consumer
+        a.fused_groups = max(1, min(env_int("COORDX_BWD_FUSED_GROUPS", max(1, cons / 2)), min(pairs, cons)));
+        a.d_inner = dfeat[C - 1];
+        CX_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)total * 4, st));
+        if (env_int("COORDX_BWD_POISON", 0))       // debugging aid: a tile consumed before it was stored turns every gradient into NaN
+          CX_CUDA(cudaMemsetAsync(base + pl.dz_off, 0xFF, (size_t)total * (4 * CH), st));
+        CX_TRY(launch_bwd_fused(a, precision, net->fusion_op, net->act, O, sms, st));
+        if (C == 3) {
+          pair_scatter_kernel<<<(unsigned)cdiv((r1 - r0) * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 0, dfeat[0]);
+          CX_LAUNCH_CHECK();
+          pair_scatter_kernel<<<(unsigned)cdiv(n1 * HD, 256), 256, 0, st>>>(drv, feats[0], feats[1], r0, r1 - r0, n1, net->fusion_op, 1, dfeat[1]);
+          CX_LAUNCH_CHECK();
+        }
+        return 0;
+      }
       CX_TRY(launch_dw2(a, precision, net->fusion_op, net->act, O, grid, st));
       if (!pl.reuse) a.outer_img = nullptr;        // (the recompute passes index their row image differently)
     }

@@ -25,6 +25,69 @@ namespace coordx {
 namespace tcb {
 
 // =================================================================================
+// the tiles of one CTA
+// =================================================================================
+// A CTA works through every `stride`-th chunk of G consecutive tiles of a range [rb, re), starting with chunk `first`.
+//  * stand-alone passes: one chunk = the CTA's whole range;
+//  * fused kernel: the CTAs form groups of P dW pairs and C feature-gradient CTAs that sweep the group's range front
+//    to back TOGETHER: chunk m of the range is computed by pair m mod P and consumed by feature-gradient CTA m mod C,
+//    a few tens of microseconds later, out of the L2.  Neighbouring chunks share the block of inner rows (jb) almost
+//    always, so the dW producers keep their inner block in registers and the feature-gradient CTAs their d(inner)
+//    accumulators, as in the stand-alone passes.  Every role of a CTA derives the same sequence on its own.
+struct TileRuns {
+  int64_t rb, re;
+  int G, m, stride;
+  __device__ static TileRuns make(int64_t rb, int64_t re, int G, int first, int stride) {
+    TileRuns r;
+    r.rb = rb; r.re = re; r.G = G; r.m = first; r.stride = stride;
+    return r;
+  }
+  __device__ static TileRuns single(int64_t b, int64_t e) {
+    return make(b, e, (int)(e - b > 0 ? e - b : 1), 0, 1);
+  }
+  __device__ bool next(int64_t& t0, int& cnt) {
+    t0 = rb + (int64_t)m * G;
+    if (t0 >= re) return false;
+    cnt = (int)(re - t0 < G ? re - t0 : G);
+    m += stride;
+    return true;
+  }
+  __device__ int count() const {                   // tiles in all chunks from m on
+    const int64_t len = re - rb;
+    if (len <= 0) return 0;
+    const int n_chunks = (int)((len + G - 1) / G);
+    if (m >= n_chunks) return 0;
+    const int mine = (n_chunks - 1 - m) / stride + 1;
+    const int last = m + (mine - 1) * stride;       // my last chunk: ragged if it is the range's last
+    return mine * G - (last == n_chunks - 1 ? (int)((int64_t)n_chunks * G - len) : 0);
+  }
+};
+
+// walks the tiles of a TileRuns one by one: (jb, o) of the current tile and of the one after it
+struct TileWalk {
+  TileRuns it;
+  int64_t t0, n_o;
+  int cnt, idx;
+  int64_t t, jb;
+  int o;
+  bool valid;
+  __device__ TileWalk(const TileRuns& r, int64_t n_o_) : it(r), n_o(n_o_), cnt(0), idx(0), t(0), jb(0), o(0) {
+    valid = it.next(t0, cnt);
+    if (valid) { t = t0; jb = t0 / n_o; o = (int)(t0 - jb * n_o); }
+  }
+  __device__ void advance() {
+    if (++idx < cnt) {
+      ++t;
+      if (++o == (int)n_o) { o = 0; ++jb; }
+    } else {
+      idx = 0;
+      valid = it.next(t0, cnt);
+      if (valid) { t = t0; jb = t0 / n_o; o = (int)(t0 - jb * n_o); }
+    }
+  }
+};
+
+// =================================================================================
 // dW pass, second version
 // =================================================================================
 constexpr int D2_STAGES = 3;
@@ -82,10 +145,10 @@ __device__ __forceinline__ void sincos_rev_x2(uint64_t t2, uint64_t& sn, uint64_
   pc = ptx::fma_f32x2(pc, q2, f2x(-19.731046676635742f));
   cs = ptx::fma_f32x2(pc, q2, f2x(0.9999598264694214f));
 }
+// One CTA's share of the dW pass: half h of the output features, the tiles of `runs`.  p.flags != nullptr (fused
+// kernel): the store warp counts every completed sub-tile store into flags[tile] for the feature-gradient CTAs.
 template <typename T, int OP, int ACT, int O>
-__global__ void __launch_bounds__(DW2_THREADS, 1)
-trunk_bwd_dw2_kernel(const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+__device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, const int h, const TileRuns runs) {
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem_gen = smem_raw;
@@ -95,17 +158,9 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
   constexpr int W_PROD = 16, W_MMA = 24, W_STORE = 25;
   constexpr int DST = d2_dout_stages(O);
 
-  const int h = blockIdx.x & 1;                    // half of the trunk's output features
-  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
   const int64_t n_o = p.o_end - p.o_begin;
-  const int64_t total = (int64_t)p.nb * n_o;
-  const int64_t t_begin = total * cta / n_cta;
-  const int64_t t_end = total * (cta + 1) / n_cta;
-  const int my_tiles = (int)(t_end - t_begin);
+  const int my_tiles = runs.count();
   const int n_sub = 2 * my_tiles;
-  const int n_o32 = (int)n_o;
-  const int64_t jb0 = my_tiles > 0 ? t_begin / n_o : 0;
-  const int o0 = my_tiles > 0 ? (int)(t_begin - jb0 * n_o) : 0;
 
   if (warp == W_MMA) {
     if (lane == 0) {
@@ -190,17 +245,26 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
     } else if (warp == W_STORE) {
       // ============================ dZ^T image -> HBM (one 16 KB bulk store per sub-tile) ============================
       if (p.dz_img != nullptr && my_tiles > 0 && ptx::elect_one()) {
+        TileWalk w(runs, n_o);
+        int64_t t_prev = 0;                        // tile of the store issued last
         for (int s = 0; s < n_sub; ++s) {
-          const int t = s >> 1, hh = s & 1;
+          const int hh = s & 1;
           ptx::mbar_wait(B.dzfull + 8 * (s & 1), (s >> 1) & 1);
-          ptx::bulk_s2g(p.dz_img + (((size_t)(t_begin + t) * 2 + h) * 2 + hh) * CH, smem_base + D2_IMG + (s & 1) * CH, CH);
+          ptx::bulk_s2g(p.dz_img + (((size_t)w.t * 2 + h) * 2 + hh) * CH, smem_base + D2_IMG + (s & 1) * CH, CH);
           ptx::bulk_commit_group();
           // hand the chunk back as soon as the copy engine has READ it (this thread has nothing else to do): signalled
           // one store later, E1(s+2) found its chunk free only after every warp had finished sub-tile s+1
           ptx::bulk_wait_group_read<0>();
           ptx::mbar_arrive(B.imgempty + 8 * (s & 1));
+          if (p.flags != nullptr && s > 0) {       // store s - 1 has landed: publish it (one store of latency behind)
+            ptx::bulk_wait_group<1>();
+            ptx::publish_add(p.flags + t_prev);
+          }
+          t_prev = w.t;
+          if (hh == 1) w.advance();
         }
         ptx::bulk_wait_group0();
+        if (p.flags != nullptr) ptx::publish_add(p.flags + t_prev);
       }
       __syncwarp();
     }
@@ -216,15 +280,15 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
     uint32_t in[16][4];
     int64_t cur_jb = -1;
     int st = 0, use = 0, dsg = 0, dsuse = 0;
-    int64_t jb = jb0;
-    int o_local = o0;
+    TileWalk w(runs, n_o);
     const uint4* rv_rows = reinterpret_cast<const uint4*>(p.outer_img) + g;      // row o at + o * 32 (512 B per row)
-    uint4 rv_next = my_tiles > 0 ? __ldg(rv_rows + (size_t)o_local * 32) : make_uint4(0, 0, 0, 0);
+    uint4 rv_next = my_tiles > 0 ? __ldg(rv_rows + (size_t)w.o * 32) : make_uint4(0, 0, 0, 0);
     for (int t = 0; t < my_tiles; ++t) {
       const uint4 rv = rv_next;
-      int o_nxt = o_local + 1;
-      if (o_nxt == n_o32) o_nxt = 0;
-      if (t + 1 < my_tiles) rv_next = __ldg(rv_rows + (size_t)o_nxt * 32);       // in flight while this tile is written
+      const int64_t jb = w.jb;
+      const int o_local = w.o;
+      w.advance();
+      if (t + 1 < my_tiles) rv_next = __ldg(rv_rows + (size_t)w.o * 32);         // in flight while this tile is written
       float dreg[O];
 #pragma unroll
       for (int oo = 0; oo < O; ++oo) dreg[oo] = 0.f;
@@ -289,8 +353,6 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
       }
       if (++dsg == DST) { dsg = 0; ++dsuse; }
       if (ptid == 0) trace_stamp(p, 3, t, 3);
-      o_local = o_nxt;
-      if (o_nxt == 0) ++jb;
     }
   } else {
     ptx::setmaxnreg_dec<D2_REGS_E1>();
@@ -476,11 +538,10 @@ constexpr uint32_t DF_INNER = DF_DZ + DF_STAGES * 2 * CH;  // 64 KB: per-thread 
 constexpr uint32_t DF_BAR = DF_INNER + 4 * CH;
 constexpr uint32_t DF_TOTAL = DF_BAR + 256;
 constexpr int DF_THREADS = 18 * 32;                        // 0-15 E2 (group = warp >> 3 owns sub-tile hh = group) | 16 loader | 17 MMA
+constexpr int DF_REGS_E2 = 96, DF_REGS_REST = 32;          // fused kernel only (launched at 72 registers per thread)
 
-template <typename T, int OP>
-__global__ void __launch_bounds__(DF_THREADS, 1)
-trunk_bwd_dfeat_kernel(const BwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
+template <typename T, int OP, bool FUSED>
+__device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw, const TileRuns runs) {
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();
   uint8_t* smem_gen = smem_raw;
@@ -491,16 +552,7 @@ trunk_bwd_dfeat_kernel(const BwdParams p) {
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + DF_BAR + 16 * DF_STAGES + 40);
   constexpr int W_LOAD = 16, W_MMA = 17;
 
-  const int n_cta = gridDim.x, cta = blockIdx.x;
   const int64_t n_o = p.o_end - p.o_begin;
-  const int64_t total = (int64_t)p.nb * n_o;
-  const int64_t t_begin = total * cta / n_cta;
-  const int64_t t_end = total * (cta + 1) / n_cta;
-  const int my_tiles = (int)(t_end - t_begin);
-  const int n_sub = 2 * my_tiles;
-  const int n_o32 = (int)n_o;
-  const int64_t jb0 = my_tiles > 0 ? t_begin / n_o : 0;
-  const int o0 = my_tiles > 0 ? (int)(t_begin - jb0 * n_o) : 0;
 
   if (warp == W_MMA) {
     if (lane == 0) {
@@ -525,48 +577,67 @@ trunk_bwd_dfeat_kernel(const BwdParams p) {
   const uint32_t tmem_base = *tmem_slot_gen;
   const uint32_t tA = tmem_base, tAcc = tmem_base + 256;
 
+  if (warp >= 16) {
+    if (FUSED) ptx::setmaxnreg_dec<DF_REGS_REST>();
   if (warp == W_LOAD) {
     // ============================ loader: ring of dZ^T sub-tiles (h = 0 and h = 1 chunks) ============================
-    if (my_tiles > 0 && ptx::elect_one()) {
+    if (ptx::elect_one()) {
+      TileRuns it = runs;
+      int64_t t0;
+      int cnt;
       int stg = 0, use = 0;
-      for (int s = 0; s < n_sub; ++s) {
-        const int t = s >> 1, hh = s & 1;
-        ptx::mbar_wait(b_dzempty + 8 * stg, (use & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(b_dzfull + 8 * stg, 2 * CH);
-        const uint8_t* src = p.dz_img + ((size_t)(t_begin + t) * 4 + hh) * CH;
-        ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH, src, CH, b_dzfull + 8 * stg);               // h = 0
-        ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH + CH, src + 2 * CH, CH, b_dzfull + 8 * stg);  // h = 1
-        if (++stg == DF_STAGES) { stg = 0; ++use; }
+      while (it.next(t0, cnt)) {
+        for (int s = 0; s < 2 * cnt; ++s) {
+          const int64_t t = t0 + (s >> 1);
+          const int hh = s & 1;
+          if (FUSED && hh == 0) {                  // both halves, both sub-tiles of tile t stored by the dW CTAs?
+            while (ptx::ld_acquire_gpu(p.flags + t) < 4u) __nanosleep(64);
+            ptx::fence_proxy_async_all();          // the copy engine reads what the acquire made visible
+          }
+          ptx::mbar_wait(b_dzempty + 8 * stg, (use & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(b_dzfull + 8 * stg, 2 * CH);
+          const uint8_t* src = p.dz_img + ((size_t)t * 4 + hh) * CH;
+          ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH, src, CH, b_dzfull + 8 * stg);               // h = 0
+          ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH + CH, src + 2 * CH, CH, b_dzfull + 8 * stg);  // h = 1
+          if (++stg == DF_STAGES) { stg = 0; ++use; }
+        }
       }
     }
     __syncwarp();
   } else if (warp == W_MMA) {
     // ============================ MMA issuer: dH^T[k, p] = sum_n W^T[k, n] dZ^T[n, p] ============================
-    if (my_tiles > 0 && ptx::elect_one()) {
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 0, 1);   // A in tensor memory, B = dZ^T (N = 64 points) MN-major
       ptx::mbar_wait(b_wfull, 0);
       ptx::tc_fence_after();
-      int stg = 0, use = 0;
-      for (int s = 0; s < n_sub; ++s) {
-        const int hh = s & 1;
-        ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
-        ptx::mbar_wait(b_accempty + 8 * hh, ((s >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t dz = smem_base + DF_DZ + stg * 2 * CH;
+      TileRuns it = runs;
+      int64_t t0;
+      int cnt;
+      int stg = 0, use = 0, s = 0;                 // s: sub-tiles issued so far (accumulator hh = s & 1, its use count s >> 1)
+      while (it.next(t0, cnt)) {
+        for (int ss = 0; ss < 2 * cnt; ++ss, ++s) {
+          const int hh = s & 1;
+          ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
+          ptx::mbar_wait(b_accempty + 8 * hh, ((s >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t dz = smem_base + DF_DZ + stg * 2 * CH;
 #pragma unroll
-        for (int blk = 0; blk < 2; ++blk) {
+          for (int blk = 0; blk < 2; ++blk) {
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks)          // K = 256 output features n: 8 steps in the h = 0 chunk, 8 in the h = 1 chunk
-            ptx::mma_f16_ts(tAcc + hh * 128 + blk * 64, tA + blk * 128 + ks * 8,
-                            ptx::umma_desc_mn_sw128(dz + (ks >> 3) * CH + (ks & 7) * 2048, CH), idesc, ks != 0);
+            for (int ks = 0; ks < 16; ++ks)        // K = 256 output features n: 8 steps in the h = 0 chunk, 8 in the h = 1 chunk
+              ptx::mma_f16_ts(tAcc + hh * 128 + blk * 64, tA + blk * 128 + ks * 8,
+                              ptx::umma_desc_mn_sw128(dz + (ks >> 3) * CH + (ks & 7) * 2048, CH), idesc, ks != 0);
+          }
+          ptx::mma_commit(b_accfull + 8 * hh);
+          ptx::mma_commit(b_dzempty + 8 * stg);
+          if (++stg == DF_STAGES) { stg = 0; ++use; }
         }
-        ptx::mma_commit(b_accfull + 8 * hh);
-        ptx::mma_commit(b_dzempty + 8 * stg);
-        if (++stg == DF_STAGES) { stg = 0; ++use; }
       }
     }
     __syncwarp();
+  }
   } else {
+    if (FUSED) ptx::setmaxnreg_inc<DF_REGS_E2>();
     // ============================ E2: dH^T sub-tile -> d rowvec(o) (atomics per tile) and d inner (registers) ============================
     const int g = warp >> 3, q = warp & 3, blk = (warp >> 2) & 1;
     const int k = blk * 128 + q * 32 + lane;
@@ -618,18 +689,23 @@ trunk_bwd_dfeat_kernel(const BwdParams p) {
       const uint32_t e = __ldg(reinterpret_cast<const uint16_t*>(p.outer_img) + (size_t)o_local * HD + k);
       return Pack<T>::unpack(e, 0);
     };
-    int64_t jb = jb0;
-    int o_local = o0;
-    if (OP == COORDX_FUSE_PROD && my_tiles > 0) load_inner(jb);
-    float rv_next = my_tiles > 0 ? load_rv(o_local) : 0.f;
-    for (int t = 0; t < my_tiles; ++t) {
+    TileWalk w(runs, n_o);
+    int64_t cur_jb = -1;                           // block of inner rows whose 16-bit column is staged / whose d(inner) sums are live
+    bool dirty = false;
+    float rv_next = w.valid ? load_rv(w.o) : 0.f;
+    for (int tc = 0; w.valid; ++tc) {              // tc: tiles done so far (accumulator phase)
       const float rv = rv_next;
-      {
-        int on = o_local + 1;
-        if (on == n_o32) on = 0;
-        if (t + 1 < my_tiles) rv_next = load_rv(on);                   // in flight during this tile
+      const int64_t jb = w.jb;
+      const int o_local = w.o;
+      w.advance();
+      if (w.valid) rv_next = load_rv(w.o);                             // in flight during this tile
+      if (jb != cur_jb) {                          // new block of inner rows (stand-alone pass: the sweep over o is complete)
+        if (dirty) flush_din(cur_jb);
+        dirty = false;
+        if (OP == COORDX_FUSE_PROD) load_inner(jb);
+        cur_jb = jb;
       }
-      ptx::mbar_wait(b_accfull + 8 * g, t & 1);
+      ptx::mbar_wait(b_accfull + 8 * g, tc & 1);
       ptx::tc_fence_after();
       float acc2[2] = {0.f, 0.f};
       const uint32_t tacc = tAcc + g * 128 + blk * 64 + lane_base;
@@ -652,8 +728,8 @@ trunk_bwd_dfeat_kernel(const BwdParams p) {
           const float dh = __uint_as_float(r[i]);
           if (OP == COORDX_FUSE_PROD) {
             const uint4 v = iv[i >> 3];
-            const uint32_t w = ((i >> 1) & 3) == 0 ? v.x : (((i >> 1) & 3) == 1 ? v.y : (((i >> 1) & 3) == 2 ? v.z : v.w));
-            acc2[i & 1] = fmaf(dh, Pack<T>::unpack(w, i & 1), acc2[i & 1]);
+            const uint32_t w16 = ((i >> 1) & 3) == 0 ? v.x : (((i >> 1) & 3) == 1 ? v.y : (((i >> 1) & 3) == 2 ? v.z : v.w));
+            acc2[i & 1] = fmaf(dh, Pack<T>::unpack(w16, i & 1), acc2[i & 1]);
             din[b * 16 + i] = fmaf(rv, dh, din[b * 16 + i]);
           } else {
             acc2[i & 1] += dh;
@@ -662,14 +738,9 @@ trunk_bwd_dfeat_kernel(const BwdParams p) {
         }
       }
       atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (acc2[0] + acc2[1]) * ginv);
-      if (++o_local == n_o32) {                    // the sweep over the outer index is complete for this block of inner rows
-        o_local = 0;
-        flush_din(jb);
-        ++jb;
-        if (OP == COORDX_FUSE_PROD && t + 1 < my_tiles) load_inner(jb);
-      }
+      dirty = true;
     }
-    if (my_tiles > 0 && o_local != 0) flush_din(jb);
+    if (dirty) flush_din(cur_jb);
   }
 
   ptx::tc_fence_before();
@@ -680,9 +751,98 @@ trunk_bwd_dfeat_kernel(const BwdParams p) {
   }
 }
 
+// =================================================================================
+// kernels: the two passes on their own, and both in ONE launch
+// =================================================================================
+template <typename T, int OP, int ACT, int O>
+__global__ void __launch_bounds__(DW2_THREADS, 1)
+trunk_bwd_dw2_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int h = blockIdx.x & 1;                    // half of the trunk's output features
+  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
+  const int64_t total = (int64_t)p.nb * (p.o_end - p.o_begin);
+  dw2_body<T, OP, ACT, O>(p, smem_raw, h, TileRuns::single(total * cta / n_cta, total * (cta + 1) / n_cta));
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(DF_THREADS, 1)
+trunk_bwd_dfeat_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int n_cta = gridDim.x, cta = blockIdx.x;
+  const int64_t total = (int64_t)p.nb * (p.o_end - p.o_begin);
+  dfeat_body<T, OP, false>(p, smem_raw, TileRuns::single(total * cta / n_cta, total * (cta + 1) / n_cta));
+}
+
+// Fused backward: CTAs 0 .. 2 p.fused_pairs - 1 run the dW pass (pair = blockIdx / 2, its two CTAs the two halves of the
+// output features), the remaining CTAs run the feature-gradient pass BEHIND them on the tiles the pairs have already
+// stored.  Run back to back, the dW pass is bound by the MUFU / tensor pipes (HBM idle but for 2 GB of writes) and the
+// feature-gradient pass by HBM (2.1 GB read at ~4.8 TB/s, tensor pipe 30 %, profiles/r02b_bwd_dfeat_full.txt); side
+// by side the dZ^T tiles are consumed out of the L2 shortly after they were written.  The CTAs form p.fused_groups
+// groups (pairs and consumers dealt out evenly); a group sweeps its own range of tiles - sized by its number of
+// pairs - as described at TileRuns.  One CTA per SM and a grid of at most the SM count keep every CTA resident; the
+// dW CTAs have the lower block indices and never wait for anybody, so a consumer's spin always ends.
+template <typename T, int OP, int ACT, int O>
+__global__ void __launch_bounds__(DW2_THREADS, 1)
+trunk_bwd_fused_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int64_t total = (int64_t)p.nb * (p.o_end - p.o_begin);
+  const int n_pairs = p.fused_pairs, n_prod = 2 * n_pairs, n_cons = (int)gridDim.x - n_prod, NG = p.fused_groups;
+  const bool prod = (int)blockIdx.x < n_prod;
+  const int me = prod ? (int)blockIdx.x >> 1 : (int)blockIdx.x - n_prod;       // pair index / consumer index
+  const int n_mine = prod ? n_pairs : n_cons;
+  int g = (int)(((int64_t)me * NG) / n_mine);      // group g holds members [n g / NG, n (g + 1) / NG) of either kind
+  while (g + 1 < NG && (int64_t)n_mine * (g + 1) / NG <= me) ++g;
+  while (g > 0 && (int64_t)n_mine * g / NG > me) --g;
+  const int p0 = (int)((int64_t)n_pairs * g / NG), p1 = (int)((int64_t)n_pairs * (g + 1) / NG);
+  const int c0 = (int)((int64_t)n_cons * g / NG), c1 = (int)((int64_t)n_cons * (g + 1) / NG);
+  const int64_t rb = total * p0 / n_pairs, re = total * p1 / n_pairs;
+  const int G = p.fused_chunk < 0 ? -p.fused_chunk : p.fused_chunk;      // (< 0: timing aid, the consumers do nothing)
+  if (prod) {
+    dw2_body<T, OP, ACT, O>(p, smem_raw, blockIdx.x & 1, TileRuns::make(rb, re, G, me - p0, p1 - p0));
+  } else {
+    dfeat_body<T, OP, true>(p, smem_raw, TileRuns::make(rb, c1 > c0 && p.fused_chunk > 0 ? re : rb, G, me - c0, c1 - c0));
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+template <typename T, int OP, int ACT, int O>
+static int launch_fused_inst(const BwdParams& bp, int grid, cudaStream_t st) {
+  static AttrOnce once;
+  auto kern = trunk_bwd_fused_kernel<T, OP, ACT, O>;
+  constexpr uint32_t smem = d2_smem_bytes(O) > DF_TOTAL ? d2_smem_bytes(O) : DF_TOTAL;
+  CX_TRY(once.set(kern, (int)smem));
+  kern<<<grid, DW2_THREADS, smem, st>>>(bp);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T, int OP, int ACT>
+static int launch_fused_o(const BwdParams& bp, int O, int grid, cudaStream_t st) {
+  switch (O) {
+    case 1: return launch_fused_inst<T, OP, ACT, 1>(bp, grid, st);
+    case 2: return launch_fused_inst<T, OP, ACT, 2>(bp, grid, st);
+    case 3: return launch_fused_inst<T, OP, ACT, 3>(bp, grid, st);
+    case 4: return launch_fused_inst<T, OP, ACT, 4>(bp, grid, st);
+  }
+  return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk backward: out width %s%lld > 4", "", O);
+}
+
+template <typename T>
+static int launch_fused_t(const BwdParams& bp, int op, int act, int O, int grid, cudaStream_t st) {
+  if (op == COORDX_FUSE_PROD)
+    return act == COORDX_ACT_SINE ? launch_fused_o<T, COORDX_FUSE_PROD, COORDX_ACT_SINE>(bp, O, grid, st)
+                                  : launch_fused_o<T, COORDX_FUSE_PROD, COORDX_ACT_RELU>(bp, O, grid, st);
+  return act == COORDX_ACT_SINE ? launch_fused_o<T, COORDX_FUSE_SUM, COORDX_ACT_SINE>(bp, O, grid, st)
+                                : launch_fused_o<T, COORDX_FUSE_SUM, COORDX_ACT_RELU>(bp, O, grid, st);
+}
+
+int launch_bwd_fused(const BwdParams& bp, int precision, int op, int act, int O, int grid, cudaStream_t st) {
+  if (precision == COORDX_PREC_BF16) return launch_fused_t<__nv_bfloat16>(bp, op, act, O, grid, st);
+  return launch_fused_t<__half>(bp, op, act, O, grid, st);
+}
+
 template <typename T, int OP, int ACT, int O>
 static int launch_dw2_inst(const BwdParams& bp, int grid, cudaStream_t st) {
   static AttrOnce once;
