@@ -330,13 +330,11 @@ int coordx_profile_enable(int on) {
 // device buffer of 4 x 96 x 4 int64 that CTA 0 of the forward trunk kernel fills with SM-clock stamps of its
 // pipeline events (roles: MMA issuer, epilogue 0/1, producer warp 8); nullptr switches it off
 int coordx_profile_set_trace(void* dev_buf) {
-  tc::profile_set_trace(dev_buf);
-  return 0;
+  return tc::profile_set_trace(dev_buf);
 }
 // same for the backward trunk kernels; pass: 0 = dW pass, 1 = dH pass (outer axes), 2 = dH pass (last axis)
 int coordx_profile_set_bwd_trace(void* dev_buf, int pass) {
-  tc::profile_set_bwd_trace(dev_buf, pass);
-  return 0;
+  return tc::profile_set_bwd_trace(dev_buf, pass);
 }
 
 // milliseconds of the last profiled trunk kernel (synchronises on its end event)

@@ -277,6 +277,17 @@ __device__ __forceinline__ void mma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with the A operand in TENSOR MEMORY: every CTA of the pair reads the 128 rows of A held by its own lanes
+__device__ __forceinline__ void mma_f16_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // all previously issued cta_group::2 MMAs arrive on the mbarrier at this smem offset in every CTA of `mask`
 __device__ __forceinline__ void mma_commit_2cta(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

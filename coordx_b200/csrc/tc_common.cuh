@@ -6,6 +6,13 @@
 namespace coordx {
 namespace tc {
 
+// Pipeline tracing (SM-clock stamps written by CTA 0 of the trunk kernels; scripts/*_trace.py) is a BUILD option:
+// the run-time "is a trace buffer set?" checks alone cost the dW pass 6 % (963 -> 909 us per 2048^2,
+// profiles/r02i_trace_cost.txt).  scripts/build_trace_lib.sh builds coordx_b200/_build/libcoordx_trace.so with
+// -DCOORDX_TRACE=1; the product library refuses coordx_profile_set_trace / _set_bwd_trace with a buffer.
+#ifndef COORDX_TRACE
+#define COORDX_TRACE 0
+#endif
 constexpr int HD = 256;
 constexpr int TILE_M = 128;
 constexpr int KCHUNK = 64;                          // one SWIZZLE_128B row of 16-bit elements
@@ -62,8 +69,8 @@ size_t fwd_workspace_bytes(int64_t n_inner);
 int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
                      int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 void profile_enable(bool on);
-void profile_set_trace(void* dev_buf);
-void profile_set_bwd_trace(void* dev_buf, int pass);
+int profile_set_trace(void* dev_buf);
+int profile_set_bwd_trace(void* dev_buf, int pass);
 int profile_last_ms(float* ms_host);
 
 size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1, bool minimal);

@@ -69,7 +69,9 @@ constexpr int CONST_FLOATS = CONST_SCALE + 8;
 
 constexpr int TRACE_ITERS = 96;
 __device__ __forceinline__ void trace_stamp(const BwdParams& p, int role, int it, int slot) {
+#if COORDX_TRACE
   if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_ITERS) p.trace[(role * TRACE_ITERS + it) * 4 + slot] = clock64();
+#endif
 }
 
 

@@ -1572,7 +1572,6 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
     if (pl.reuse && !v1) {
       // ---------------- dfeat pass: BOTH feature gradients from the stored dZ^T tiles, one GEMM per tile
       a.d_inner = dfeat[C - 1];
-      a.trace = nullptr;
       CX_TRY(launch_dfeat(a, precision, net->fusion_op, (int)min((int64_t)num_sms(), total), st));
     } else if (pl.reuse) {
       CX_TRY((launch_drv<T>(a, net->fusion_op, grid, st)));
@@ -1629,7 +1628,14 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
 
 namespace coordx {
 namespace tc {
-void profile_set_bwd_trace(void* dev_buf, int pass) { tcb::g_bwd_trace = (long long*)dev_buf; tcb::g_bwd_trace_pass = pass; }
+int profile_set_bwd_trace(void* dev_buf, int pass) {
+#if !COORDX_TRACE
+  if (dev_buf) return set_err(COORDX_ERR_UNSUPPORTED, "pipeline tracing is a build option%s (scripts/build_trace_lib.sh, -DCOORDX_TRACE=1)");
+#endif
+  tcb::g_bwd_trace = (long long*)dev_buf;
+  tcb::g_bwd_trace_pass = pass;
+  return 0;
+}
 size_t bwd_workspace_bytes(const coordx_net* net, const int64_t* n, int64_t r0, int64_t r1, bool minimal) {
   const tcb::BwdPlan small = tcb::plan_bwd(net, n, r0, r1, false);
   if (minimal || !tcb::dz_reuse_wanted((int64_t)small.nbA * small.n_oA)) return small.total;

@@ -104,6 +104,13 @@ constexpr int DW2_THREADS = 28 * 32;
 #define COORDX_DW2_NPOLY 2          // of the 8 (even, odd) pairs of a thread's 16 values, how many take the FMA-pipe polynomial
 #endif
 constexpr int D2_E1_ARRIVALS = 16;      // one elected arrive per E1 warp
+// CTA-pair form: how the leader learns that the PEER's producers / E1 warps are done with a (sub-)tile.
+// 1: the peer's otherwise idle warps 24 / 26 wait on the peer's own barriers and forward ONE remote arrive each, so
+//    producers and E1 warps signal exactly as in the single-CTA form; 0: every producer / E1 warp arrives remotely.
+#ifndef COORDX_DW3_FORWARD
+#define COORDX_DW3_FORWARD 0        // measured: 1035 us (forwarded) vs 1024 us (direct) per 2048^2, profiles/r02g_dw_pair.txt
+#endif
+constexpr bool D3_FWD = COORDX_DW3_FORWARD != 0;
 __host__ __device__ constexpr bool d2_poly_pair(int e2) {
   return (e2 * COORDX_DW2_NPOLY) / 8 != ((e2 + 1) * COORDX_DW2_NPOLY) / 8;
 }
@@ -118,9 +125,11 @@ struct Bars2 {
   uint32_t imgempty;           // [2] the bulk store has read the image chunk
   uint32_t dsfull, dsempty;    // [2] dout staging
   uint32_t wfull, dwfull, tmem_slot;
+  uint32_t dzpair;             // [2] CTA-pair form, leader only: dZ^T written by the E1 warps of the peer (forwarded) / of both CTAs
+  uint32_t fullpeer;           // [3] CTA-pair form, leader only: the peer's H stage is written (forwarded)
   __device__ explicit Bars2(uint32_t b0)
       : full(b0), empty(b0 + 24), zfull(b0 + 48), dzfull(b0 + 64), imgempty(b0 + 80), dsfull(b0 + 96), dsempty(b0 + 112),
-        wfull(b0 + 128), dwfull(b0 + 136), tmem_slot(b0 + 144) {}
+        wfull(b0 + 128), dwfull(b0 + 136), tmem_slot(b0 + 144), dzpair(b0 + 160), fullpeer(b0 + 176) {}
 };
 
 // sin(2 pi r) and cos(2 pi r) on r in [-1/2, 1/2] (r = fractional part of the angle in revolutions), two values per
@@ -147,7 +156,16 @@ __device__ __forceinline__ void sincos_rev_x2(uint64_t t2, uint64_t& sn, uint64_
 }
 // One CTA's share of the dW pass: half h of the output features, the tiles of `runs`.  p.flags != nullptr (fused
 // kernel): the store warp counts every completed sub-tile store into flags[tile] for the feature-gradient CTAs.
-template <typename T, int OP, int ACT, int O>
+//
+// PAIR = true (trunk_bwd_dw3_kernel): the two CTAs that own the two halves of the output features are a cluster and
+// work on the SAME tile at the same time; both GEMMs are cta_group::2 instructions issued by the leader (h = 0):
+//   G1  Z^T [256 n x 64 points] : A = W_h in each CTA's tensor memory, B (N = points) 32 points from each CTA;
+//   G3  dW  [256 n x 256 k]     : A = dZ^T in each CTA's tensor memory, B (N = k) 128 columns from each CTA.
+// Every tensor core then fetches HALF of each B operand from its own shared memory (32 B/clk instead of 64 B/clk,
+// which is the measured fetch limit of SS/TS MMAs, section 3.2 of DESIGN.md) and receives the other half from the
+// peer.  A CTA's H stage holds [all 128 points x its 128 k] (chunks 0-1, the G3 operand) and [its 2 x 32 points x
+// 256 k] (chunks 2-3 re-organised as [4 k-chunks][2 sub-tiles][32 rows], the G1 operand): 64 KB as before.
+template <typename T, int OP, int ACT, int O, bool PAIR>
 __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, const int h, const TileRuns runs) {
   const uint32_t smem_base = ptx::smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();          // SWIZZLE_128B atoms need 1024-byte alignment
@@ -165,37 +183,52 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
   if (warp == W_MMA) {
     if (lane == 0) {
       for (int c = 0; c < D2_STAGES; ++c) {
-        ptx::mbar_init(B.full + 8 * c, 8);         // 8 producer warps
+        ptx::mbar_init(B.full + 8 * c, PAIR && !D3_FWD ? 16 : 8);   // 8 producer warps (of each CTA)
+        ptx::mbar_init(B.fullpeer + 8 * c, 1);
         ptx::mbar_init(B.empty + 8 * c, 1);
       }
       for (int c = 0; c < 2; ++c) {
         ptx::mbar_init(B.zfull + 8 * c, 1);
         ptx::mbar_init(B.dzfull + 8 * c, D2_E1_ARRIVALS);
+        ptx::mbar_init(B.dzpair + 8 * c, D3_FWD ? 1 : 2 * D2_E1_ARRIVALS);
         ptx::mbar_init(B.imgempty + 8 * c, 1);
         ptx::mbar_init(B.dsfull + 8 * c, 128);
         ptx::mbar_init(B.dsempty + 8 * c, D2_E1_ARRIVALS);
       }
-      ptx::mbar_init(B.wfull, 512);
+      ptx::mbar_init(B.wfull, PAIR ? 1024 : 512);
       ptx::mbar_init(B.dwfull, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(B.tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_2cta(B.tmem_slot, 512);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(B.tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync();                   // the peer's barriers and tensor memory exist
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   const uint32_t tZ = tmem_base, tW = tmem_base + 128, tDW = tmem_base + 256;
+  auto mma_ts = [](uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (PAIR) ptx::mma_f16_ts_2cta(d, a, b, idesc, acc); else ptx::mma_f16_ts(d, a, b, idesc, acc);
+  };
+  auto commit = [](uint32_t bar) {
+    if (PAIR) ptx::mma_commit_2cta(bar, 3); else ptx::mma_commit(bar);
+  };
 
   if (warp >= W_MMA) {
     ptx::setmaxnreg_dec<D2_REGS_MMA>();
     if (warp == W_MMA) {
       // ============================ MMA issuer ============================
-      if (my_tiles > 0 && ptx::elect_one()) {     // (elect, not lane == 0: see ptx::elect_one)
-        constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 64, 0, 0);    // A = W_h (TMEM, M = n_out), B = H (N = 64 points) K-major
-        constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, 128, 256, 0, 1);   // A = dZ^T (TMEM, M = n_out), B = H (N = k_in) MN-major
+      if ((!PAIR || h == 0) && my_tiles > 0 && ptx::elect_one()) {     // (elect, not lane == 0: see ptx::elect_one)
+        constexpr uint32_t MM = PAIR ? 256 : 128;
+        constexpr uint32_t id_g1 = ptx::umma_idesc_f16(Pack<T>::kFmt, MM, 64, 0, 0);    // A = W_h (TMEM, M = n_out), B = H (N = 64 points) K-major
+        constexpr uint32_t id_g3 = ptx::umma_idesc_f16(Pack<T>::kFmt, MM, 256, 0, 1);   // A = dZ^T (TMEM, M = n_out), B = H (N = k_in) MN-major
         ptx::mbar_wait(B.wfull, 0);
         ptx::tc_fence_after();
         int st1 = 0, use1 = 0;                     // H stage / use count of the tile G1 works on
@@ -206,27 +239,31 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
           const uint32_t zb = s & 1, hh = s & 1;
           if (hh == 0) {
             ptx::mbar_wait(B.full + 8 * st1, use1 & 1);
+            if (PAIR && D3_FWD) ptx::mbar_wait(B.fullpeer + 8 * st1, use1 & 1);
             ptx::tc_fence_after();
           }
           // (no wait for the Z^T buffer: its last reader G3(s-2) is earlier in this thread's in-order tensor pipe)
-          const uint32_t hs = smem_base + D2_H + st1 * 4 * CH + hh * 8192;     // rows 64 hh .. 64 hh + 63 of every chunk
+          // rows 64 hh .. 64 hh + 63 of every chunk | pair: this CTA's 32 rows of sub-tile hh, k-chunks 8 KB apart
+          const uint32_t hs = PAIR ? smem_base + D2_H + st1 * 4 * CH + 2 * CH + hh * 4096 : smem_base + D2_H + st1 * 4 * CH + hh * 8192;
+          constexpr uint32_t KC = PAIR ? 8192 : CH;
 #pragma unroll
           for (int k = 0; k < 16; ++k)
-            ptx::mma_f16_ts(tZ + zb * 64, tW + k * 8, ptx::umma_desc_k_sw128(hs + (k >> 2) * CH + (k & 3) * 32), id_g1, k != 0);
-          ptx::mma_commit(B.zfull + 8 * zb);
+            mma_ts(tZ + zb * 64, tW + k * 8, ptx::umma_desc_k_sw128(hs + (k >> 2) * KC + (k & 3) * 32), id_g1, k != 0);
+          commit(B.zfull + 8 * zb);
           if (hh == 1 && ++st1 == D2_STAGES) { st1 = 0; ++use1; }
         };
         auto issue_g3 = [&](int s) {
           const uint32_t zb = s & 1, hh = s & 1;
-          ptx::mbar_wait(B.dzfull + 8 * zb, (s >> 1) & 1);
+          if (!PAIR || D3_FWD) ptx::mbar_wait(B.dzfull + 8 * zb, (s >> 1) & 1);
+          if (PAIR) ptx::mbar_wait(B.dzpair + 8 * zb, (s >> 1) & 1);
           trace_stamp(p, 0, s, 2);
           ptx::tc_fence_after();
-          const uint32_t hs = smem_base + D2_H + st3 * 4 * CH;
+          const uint32_t hs = smem_base + D2_H + st3 * 4 * CH;         // (pair: chunks 0-1 = this CTA's 128 k)
 #pragma unroll
           for (int j = 0; j < 4; ++j)              // K = 64 points, 16 per step: E1 column group j wrote its dZ^T pairs over its first 8 columns
-            ptx::mma_f16_ts(tDW, tZ + zb * 64 + j * 16, ptx::umma_desc_mn_sw128(hs + (hh * 4 + j) * 2048, CH), id_g3, (s | j) != 0);
+            mma_ts(tDW, tZ + zb * 64 + j * 16, ptx::umma_desc_mn_sw128(hs + (hh * 4 + j) * 2048, CH), id_g3, (s | j) != 0);
           if (hh == 1) {
-            ptx::mma_commit(B.empty + 8 * st3);    // H stage free for the producers
+            commit(B.empty + 8 * st3);             // H stage free for the producers
             if (++st3 == D2_STAGES) st3 = 0;
           }
         };
@@ -239,7 +276,29 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
           issue_g3(s);
           trace_stamp(p, 0, s, 3);
         }
-        ptx::mma_commit(B.dwfull);
+        commit(B.dwfull);
+      }
+      if (PAIR && D3_FWD && h == 1 && my_tiles > 0 && ptx::elect_one()) {
+        // peer CTA: forward "dZ^T of sub-tile s is in this CTA's tensor memory" to the leader's MMA thread
+        const uint32_t remote = ptx::mapa(B.dzpair, 0);
+        for (int s = 0; s < n_sub; ++s) {
+          ptx::mbar_wait(B.dzfull + 8 * (s & 1), (s >> 1) & 1);
+          ptx::tc_fence_after();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive_cluster(remote + 8 * (s & 1));
+        }
+      }
+      __syncwarp();
+    } else if (PAIR && D3_FWD && warp == W_STORE + 1) {
+      if (h == 1 && my_tiles > 0 && ptx::elect_one()) {
+        // peer CTA: forward "H stage written by this CTA's producers"
+        const uint32_t remote = ptx::mapa(B.fullpeer, 0);
+        int st = 0, use = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+          ptx::mbar_wait(B.full + 8 * st, use & 1);
+          ptx::mbar_arrive_cluster(remote + 8 * st);
+          if (++st == D2_STAGES) { st = 0; ++use; }
+        }
       }
       __syncwarp();
     } else if (warp == W_STORE) {
@@ -329,19 +388,57 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
       if (ptid == 0) trace_stamp(p, 3, t, 0);
       ptx::mbar_wait(B.empty + 8 * st, (use & 1) ^ 1);
       if (ptid == 0) trace_stamp(p, 3, t, 1);
-      uint8_t* dst = smem_gen + D2_H + (uint32_t)st * 4 * CH + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
+      if (!PAIR) {
+        uint8_t* dst = smem_gen + D2_H + (uint32_t)st * 4 * CH + (uint32_t)(g >> 3) * CH + (uint32_t)rg * 2048u;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        uint4 w;
-        w.x = fuse2<T, OP>(in[r][0], rv.x);
-        w.y = fuse2<T, OP>(in[r][1], rv.y);
-        w.z = fuse2<T, OP>(in[r][2], rv.z);
-        w.w = fuse2<T, OP>(in[r][3], rv.w);
-        *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+        for (int r = 0; r < 16; ++r) {
+          uint4 w;
+          w.x = fuse2<T, OP>(in[r][0], rv.x);
+          w.y = fuse2<T, OP>(in[r][1], rv.y);
+          w.z = fuse2<T, OP>(in[r][2], rv.z);
+          w.w = fuse2<T, OP>(in[r][3], rv.w);
+          *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(B.full + 8 * st);
+      } else {
+        // G3 operand (chunks 0-1): every row, the pieces of this CTA's 128 k (half of the lanes);
+        // G1 operand (chunks 2-3): every piece, the rows of this CTA's 32-point blocks (half of the warps)
+        uint8_t* stage = smem_gen + D2_H + (uint32_t)st * 4 * CH;
+        const bool mine_k = (g >> 4) == h;
+        const bool mine_p = ((rg >> 1) & 1) == h;
+        // two passes of the single-CTA loop (one base address live at a time: with both, the inner block spilled)
+        if (mine_k) {
+          uint8_t* dst = stage + (uint32_t)((g >> 3) & 1) * CH + (uint32_t)rg * 2048u;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            uint4 w;
+            w.x = fuse2<T, OP>(in[r][0], rv.x);
+            w.y = fuse2<T, OP>(in[r][1], rv.y);
+            w.z = fuse2<T, OP>(in[r][2], rv.z);
+            w.w = fuse2<T, OP>(in[r][3], rv.w);
+            *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+          }
+        }
+        if (mine_p) {                              // (warp-uniform)
+          uint8_t* dst = stage + 2 * CH + (uint32_t)(g >> 3) * 8192u + (uint32_t)(rg >> 2) * 4096u + (uint32_t)(rg & 1) * 2048u;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            uint4 w;
+            w.x = fuse2<T, OP>(in[r][0], rv.x);
+            w.y = fuse2<T, OP>(in[r][1], rv.y);
+            w.z = fuse2<T, OP>(in[r][2], rv.z);
+            w.w = fuse2<T, OP>(in[r][3], rv.w);
+            *reinterpret_cast<uint4*>(dst + (r >> 3) * 1024 + (r & 7) * 128 + (((g & 7) ^ (r & 7)) << 4)) = w;
+          }
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (D3_FWD) ptx::mbar_arrive(B.full + 8 * st); else ptx::mbar_arrive_cluster(ptx::mapa(B.full, 0) + 8 * st);
+        }
       }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(B.full + 8 * st);
       if (ptid == 0) trace_stamp(p, 3, t, 2);
       if (++st == D2_STAGES) { st = 0; ++use; }
       if (ptid < TILE_M) {
@@ -380,7 +477,7 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
-      ptx::mbar_arrive(B.wfull);
+      if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(B.wfull, 0)); else ptx::mbar_arrive(B.wfull);
     }
     const float gscale = p.consts[CONST_SCALE], ginv = p.consts[CONST_SCALE + 1];   // power-of-two loss scale (fp16 operands)
     const float bias_n = p.consts[h * 128 + row];                 // sine: S b[n]; relu: b[n]
@@ -492,7 +589,10 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(B.dzfull + 8 * zb);
+      if (lane == 0) {
+        ptx::mbar_arrive(B.dzfull + 8 * zb);
+        if (PAIR && !D3_FWD) ptx::mbar_arrive_cluster(ptx::mapa(B.dzpair, 0) + 8 * zb);
+      }
       if (tr) trace_stamp(p, trole, s, 3);
     }
     if (my_tiles > 0) {
@@ -523,9 +623,10 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync();                   // both CTAs are done with each other's barriers / operands
   if (warp == W_MMA) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (PAIR) ptx::tmem_dealloc_2cta(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -537,8 +638,27 @@ constexpr uint32_t DF_DZ = 0;
 constexpr uint32_t DF_INNER = DF_DZ + DF_STAGES * 2 * CH;  // 64 KB: per-thread column slice of the inner block (prod)
 constexpr uint32_t DF_BAR = DF_INNER + 4 * CH;
 constexpr uint32_t DF_TOTAL = DF_BAR + 256;
-constexpr int DF_THREADS = 18 * 32;                        // 0-15 E2 (group = warp >> 3 owns sub-tile hh = group) | 16 loader | 17 MMA
-constexpr int DF_REGS_E2 = 96, DF_REGS_REST = 32;          // fused kernel only (launched at 72 registers per thread)
+// 0-15 E2 (group = warp >> 3 owns sub-tile hh = group) | 16 loader | 17 MMA | 18-19 idle (warps re-balance registers in
+// groups of four).  A scheduler's register file holds 16 K registers: with 5 warps on it the launch gets 96 per thread,
+// which left E2 (64 accumulators + a double-buffered 2 x 16-column tensor-memory load) one load in flight at a time;
+// the loader / MMA group gives its share away (32) and the E2 warps take it (112).  Fused kernel: 72 at launch, E2 96.
+#ifndef COORDX_DF_SETREG
+#define COORDX_DF_SETREG 0
+#endif
+#ifndef COORDX_DF_DOUBLE
+#define COORDX_DF_DOUBLE 0          // tensor-memory loads of E2 double-buffered (needs the 112 registers of COORDX_DF_SETREG)
+#endif
+constexpr int DF_THREADS = COORDX_DF_SETREG ? 20 * 32 : 18 * 32;
+constexpr int DF_REGS_E2 = 112, DF_REGS_E2_FUSED = 96, DF_REGS_REST = 32;
+
+// rowvec(o)[k] is fetched ONE TILE AHEAD as its raw 16-bit pattern and only turned into a float behind the
+// accumulator wait of the tile that uses it (an opaque move pins the first use there): with the conversion next to the
+// load the E2 warps sat out an L2 round trip (~1 k clk under this pass' HBM load) at the top of every tile.
+__device__ __forceinline__ uint32_t pin_after_waits(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
 
 template <typename T, int OP, bool FUSED>
 __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw, const TileRuns runs) {
@@ -578,14 +698,14 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
   const uint32_t tA = tmem_base, tAcc = tmem_base + 256;
 
   if (warp >= 16) {
-    if (FUSED) ptx::setmaxnreg_dec<DF_REGS_REST>();
+    if (FUSED || COORDX_DF_SETREG) ptx::setmaxnreg_dec<DF_REGS_REST>();
   if (warp == W_LOAD) {
     // ============================ loader: ring of dZ^T sub-tiles (h = 0 and h = 1 chunks) ============================
     if (ptx::elect_one()) {
       TileRuns it = runs;
       int64_t t0;
       int cnt;
-      int stg = 0, use = 0;
+      int stg = 0, use = 0, sl = 0;
       while (it.next(t0, cnt)) {
         for (int s = 0; s < 2 * cnt; ++s) {
           const int64_t t = t0 + (s >> 1);
@@ -594,7 +714,10 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
             while (ptx::ld_acquire_gpu(p.flags + t) < 4u) __nanosleep(64);
             ptx::fence_proxy_async_all();          // the copy engine reads what the acquire made visible
           }
+          trace_stamp(p, 3, sl, 0);
           ptx::mbar_wait(b_dzempty + 8 * stg, (use & 1) ^ 1);
+          trace_stamp(p, 3, sl, 1);
+          ++sl;
           ptx::mbar_arrive_expect_tx(b_dzfull + 8 * stg, 2 * CH);
           const uint8_t* src = p.dz_img + ((size_t)t * 4 + hh) * CH;
           ptx::bulk_g2s(smem_base + DF_DZ + stg * 2 * CH, src, CH, b_dzfull + 8 * stg);               // h = 0
@@ -617,8 +740,11 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
       while (it.next(t0, cnt)) {
         for (int ss = 0; ss < 2 * cnt; ++ss, ++s) {
           const int hh = s & 1;
+          trace_stamp(p, 0, s, 0);
           ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
+          trace_stamp(p, 0, s, 1);
           ptx::mbar_wait(b_accempty + 8 * hh, ((s >> 1) & 1) ^ 1);
+          trace_stamp(p, 0, s, 2);
           ptx::tc_fence_after();
           const uint32_t dz = smem_base + DF_DZ + stg * 2 * CH;
 #pragma unroll
@@ -630,6 +756,7 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
           }
           ptx::mma_commit(b_accfull + 8 * hh);
           ptx::mma_commit(b_dzempty + 8 * stg);
+          trace_stamp(p, 0, s, 3);
           if (++stg == DF_STAGES) { stg = 0; ++use; }
         }
       }
@@ -637,7 +764,7 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
     __syncwarp();
   }
   } else {
-    if (FUSED) ptx::setmaxnreg_inc<DF_REGS_E2>();
+    if (FUSED || COORDX_DF_SETREG) ptx::setmaxnreg_inc<FUSED ? DF_REGS_E2_FUSED : DF_REGS_E2>();
     // ============================ E2: dH^T sub-tile -> d rowvec(o) (atomics per tile) and d inner (registers) ============================
     const int g = warp >> 3, q = warp & 3, blk = (warp >> 2) & 1;
     const int k = blk * 128 + q * 32 + lane;
@@ -660,9 +787,10 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
     }
     const float ginv = p.consts[CONST_SCALE + 1];
     uint4* my_inner = reinterpret_cast<uint4*>(smem_gen + DF_INNER) + threadIdx.x;     // slot i at [i * 512 + thread]: conflict-free
-    float din[64];
+    // d(inner) sums of this thread's 64 points as 32 (even point, odd point) pairs: all E2 arithmetic is packed fp32x2
+    uint64_t din2[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) din[i] = 0.f;
+    for (int i = 0; i < 32; ++i) din2[i] = 0ull;
     auto load_inner = [&](int64_t jb) {            // this thread's column k of the 64 inner rows of its sub-tile, 16-bit
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -679,22 +807,26 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
     auto flush_din = [&](int64_t jb) {
       float* dcol = p.d_inner + (jb * TILE_M + g * 64) * HD + k;        // lanes = consecutive k: coalesced atomics
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        if (jb * TILE_M + g * 64 + i < p.n_inner) atomicAdd(dcol + (size_t)i * HD, din[i] * ginv);
-        din[i] = 0.f;
+      for (int i2 = 0; i2 < 32; ++i2) {
+        float d0, d1;
+        ptx::unpack_f32x2(din2[i2], d0, d1);
+        if (jb * TILE_M + g * 64 + 2 * i2 < p.n_inner) atomicAdd(dcol + (size_t)(2 * i2) * HD, d0 * ginv);
+        if (jb * TILE_M + g * 64 + 2 * i2 + 1 < p.n_inner) atomicAdd(dcol + (size_t)(2 * i2 + 1) * HD, d1 * ginv);
+        din2[i2] = 0ull;
       }
     };
-    auto load_rv = [&](int o_local) -> float {     // rowvec(o)[k] as the 16-bit value the forward multiplied with
-      if (OP != COORDX_FUSE_PROD) return 1.f;
-      const uint32_t e = __ldg(reinterpret_cast<const uint16_t*>(p.outer_img) + (size_t)o_local * HD + k);
-      return Pack<T>::unpack(e, 0);
+    auto load_rv = [&](int o_local) -> uint32_t {  // rowvec(o)[k]: the raw 16-bit value the forward multiplied with
+      if (OP != COORDX_FUSE_PROD) return 0u;
+      return __ldg(reinterpret_cast<const uint16_t*>(p.outer_img) + (size_t)o_local * HD + k);
     };
     TileWalk w(runs, n_o);
     int64_t cur_jb = -1;                           // block of inner rows whose 16-bit column is staged / whose d(inner) sums are live
     bool dirty = false;
-    float rv_next = w.valid ? load_rv(w.o) : 0.f;
+    uint32_t rv_next = w.valid ? load_rv(w.o) : 0u;
+    const uint32_t tacc = tAcc + g * 128 + blk * 64 + lane_base;
+    const bool tr = (warp & 7) == 0 && lane == 0;
     for (int tc = 0; w.valid; ++tc) {              // tc: tiles done so far (accumulator phase)
-      const float rv = rv_next;
+      const uint32_t rv_raw = rv_next;
       const int64_t jb = w.jb;
       const int o_local = w.o;
       w.advance();
@@ -705,39 +837,53 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
         if (OP == COORDX_FUSE_PROD) load_inner(jb);
         cur_jb = jb;
       }
+      if (tr) trace_stamp(p, 1 + g, tc, 0);
       ptx::mbar_wait(b_accfull + 8 * g, tc & 1);
+      if (tr) trace_stamp(p, 1 + g, tc, 1);
       ptx::tc_fence_after();
-      float acc2[2] = {0.f, 0.f};
-      const uint32_t tacc = tAcc + g * 128 + blk * 64 + lane_base;
+      // The 64 columns come in four batches of 16; batch b + 1 is in flight while batch b is consumed (one batch at a
+      // time exposed the tensor-memory latency four times per tile: the pass was bound by E2, not by HBM -
+      // profiles/r02h_dfeat_stage_timing.txt).
+      uint64_t acc2 = 0ull;
+      constexpr bool DBL = COORDX_DF_DOUBLE && !FUSED;
+      uint32_t r[2][16];
+      if (DBL) ptx::tmem_ld_32x32b_x16(tacc, r[0]);
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(tacc + b * 16, r);
+        if (!DBL) ptx::tmem_ld_32x32b_x16(tacc + b * 16, r[b & 1]);
         uint4 iv[2];
         if (OP == COORDX_FUSE_PROD) {
           iv[0] = my_inner[(2 * b) * 512];
           iv[1] = my_inner[(2 * b + 1) * 512];
         }
         ptx::tmem_ld_wait();
-        if (b == 3) {
+        if (b < 3) {
+          if (DBL) ptx::tmem_ld_32x32b_x16(tacc + (b + 1) * 16, r[(b + 1) & 1]);
+        } else {
           ptx::tc_fence_before();
           ptx::mbar_arrive(b_accempty + 8 * g);
+          if (tr) trace_stamp(p, 1 + g, tc, 2);
         }
+        const float rv = OP == COORDX_FUSE_PROD ? Pack<T>::unpack(pin_after_waits(rv_raw), 0) : 1.f;
+        const uint64_t rv2 = ptx::pack_f32x2(rv, rv);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float dh = __uint_as_float(r[i]);
+        for (int i2 = 0; i2 < 8; ++i2) {
+          const uint64_t dh2 = ptx::pack_f32x2(__uint_as_float(r[b & 1][2 * i2]), __uint_as_float(r[b & 1][2 * i2 + 1]));
           if (OP == COORDX_FUSE_PROD) {
-            const uint4 v = iv[i >> 3];
-            const uint32_t w16 = ((i >> 1) & 3) == 0 ? v.x : (((i >> 1) & 3) == 1 ? v.y : (((i >> 1) & 3) == 2 ? v.z : v.w));
-            acc2[i & 1] = fmaf(dh, Pack<T>::unpack(w16, i & 1), acc2[i & 1]);
-            din[b * 16 + i] = fmaf(rv, dh, din[b * 16 + i]);
+            const uint4 v = iv[i2 >> 2];
+            const uint32_t w16 = (i2 & 3) == 0 ? v.x : ((i2 & 3) == 1 ? v.y : ((i2 & 3) == 2 ? v.z : v.w));
+            acc2 = ptx::fma_f32x2(dh2, ptx::pack_f32x2(Pack<T>::unpack(w16, 0), Pack<T>::unpack(w16, 1)), acc2);
+            din2[b * 8 + i2] = ptx::fma_f32x2(rv2, dh2, din2[b * 8 + i2]);
           } else {
-            acc2[i & 1] += dh;
-            din[b * 16 + i] += dh;
+            acc2 = ptx::add_f32x2(acc2, dh2);
+            din2[b * 8 + i2] = ptx::add_f32x2(din2[b * 8 + i2], dh2);
           }
         }
       }
-      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (acc2[0] + acc2[1]) * ginv);
+      float a0, a1;
+      ptx::unpack_f32x2(acc2, a0, a1);
+      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (a0 + a1) * ginv);
+      if (tr) trace_stamp(p, 1 + g, tc, 3);
       dirty = true;
     }
     if (dirty) flush_din(cur_jb);
@@ -752,6 +898,260 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
 }
 
 // =================================================================================
+// feature-gradient pass as CTA pairs
+// =================================================================================
+// The pipeline trace of the single-CTA pass (scripts/dfeat_trace.py, profiles/r02i_dfeat_trace.txt) shows what bounds
+// it: neither HBM (the loader waits ~1.1 k clk per sub-tile for a free stage) nor E2 (it waits 0.7-1.4 k clk per tile
+// for its accumulator) but the tensor pipe, whose M128 x N64 x K16 MMAs take 44.5 clk instead of 32: every MMA fetches
+// 2 KB of dZ^T from shared memory - 64 B/clk at full rate, the ~70 B/clk fetch limit of section 3.2 in DESIGN.md
+// next to the 23 B/clk the copy engine writes - and the tile is fetched TWICE, once per 128-row block of W^T.
+// Here the two row blocks belong to the two CTAs of a cluster: one cta_group::2 MMA M256 (k) x N128 (the points of a
+// whole tile) x K16 (n) per step, A = this CTA's half of W^T in its tensor memory (128 columns), B = dZ^T with each
+// CTA supplying ONE 64-point sub-tile image (so a CTA also loads only half of every tile from HBM).  Operand fetch per
+// SM: 2 KB per 64 clk.  The accumulator of a tile is [128 k x 128 points] = 128 columns: three of them rotate.
+constexpr int DP_STAGES = 6;                               // ring of sub-tile images (2 x 16 KB: both halves of n)
+constexpr int DP_ACC = 3;
+constexpr uint32_t DP_DZ = 0;
+constexpr uint32_t DP_INNER = DP_DZ + DP_STAGES * 2 * CH;  // 32 KB: per-thread column slice (32 points) of the inner block
+constexpr uint32_t DP_BAR = DP_INNER + 2 * CH;
+constexpr uint32_t DP_TOTAL = DP_BAR + 256;
+constexpr int DP_THREADS = 18 * 32;                        // 0-15 E2 (lane quadrant = warp & 3, 32-point column group = warp >> 2) | 16 loader | 17 MMA (leader) / forwarder (peer)
+
+template <typename T, int OP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DP_THREADS, 1)
+trunk_bwd_dfeat_pair_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  uint8_t* smem_gen = smem_raw;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();    // = the 128-row block of W^T (features k) this CTA owns
+  const uint32_t bar0 = smem_base + DP_BAR;
+  const uint32_t b_dzfull = bar0;                            // [6] this CTA's sub-tile image has landed (complete_tx)
+  const uint32_t b_dzpeer = bar0 + 8 * DP_STAGES;            // [6] leader only: the peer's image has landed (forwarded)
+  const uint32_t b_dzempty = bar0 + 16 * DP_STAGES;          // [6] each CTA: the MMAs reading the stage are complete (multicast commit)
+  const uint32_t b_accfull = bar0 + 24 * DP_STAGES;          // [3] each CTA: accumulator complete (multicast commit)
+  const uint32_t b_accempty = b_accfull + 8 * DP_ACC;        // [3] leader only: 32 E2 warps (16 per CTA) have drained it
+  const uint32_t b_wfull = b_accempty + 8 * DP_ACC;          // leader only: W^T of both CTAs is in tensor memory
+  const uint32_t b_slot = b_wfull + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + DP_BAR + 24 * DP_STAGES + 16 * DP_ACC + 8);
+  constexpr int W_LOAD = 16, W_MMA = 17;
+
+  const int64_t n_o = p.o_end - p.o_begin;
+  const int64_t total = (int64_t)p.nb * n_o;
+  const int n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const TileRuns runs = TileRuns::single(total * pair / n_pairs, total * (pair + 1) / n_pairs);
+  const int my_tiles = runs.count();
+
+  if (warp == W_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < DP_STAGES; ++s) {
+        ptx::mbar_init(b_dzfull + 8 * s, 1);
+        ptx::mbar_init(b_dzpeer + 8 * s, 1);
+        ptx::mbar_init(b_dzempty + 8 * s, 1);
+      }
+      for (int c = 0; c < DP_ACC; ++c) {
+        ptx::mbar_init(b_accfull + 8 * c, 1);
+        ptx::mbar_init(b_accempty + 8 * c, 32);
+      }
+      ptx::mbar_init(b_wfull, 1024);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc_2cta(b_slot, 512);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                             // the peer's barriers and tensor memory exist
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const uint32_t tA = tmem_base, tAcc = tmem_base + 128;
+
+  if (warp == W_LOAD) {
+    // ============================ loader: this CTA's sub-tile (hh = rank) of every tile ============================
+    if (ptx::elect_one()) {
+      TileWalk w(runs, n_o);
+      int stg = 0, use = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        ptx::mbar_wait(b_dzempty + 8 * stg, (use & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(b_dzfull + 8 * stg, 2 * CH);
+        const uint8_t* src = p.dz_img + ((size_t)w.t * 4 + rank) * CH;
+        ptx::bulk_g2s(smem_base + DP_DZ + stg * 2 * CH, src, CH, b_dzfull + 8 * stg);               // h = 0
+        ptx::bulk_g2s(smem_base + DP_DZ + stg * 2 * CH + CH, src + 2 * CH, CH, b_dzfull + 8 * stg);  // h = 1
+        if (++stg == DP_STAGES) { stg = 0; ++use; }
+        w.advance();
+      }
+    }
+    __syncwarp();
+  } else if (warp == W_MMA) {
+    if (rank == 0) {
+      // ============================ MMA issuer (leader): dH^T[k, p] = sum_n W^T[k, n] dZ^T[n, p] ============================
+      if (ptx::elect_one()) {
+        constexpr uint32_t idesc = ptx::umma_idesc_f16(Pack<T>::kFmt, 256, 128, 0, 1);   // A in tensor memory, B = dZ^T (N = points) MN-major
+        ptx::mbar_wait(b_wfull, 0);
+        ptx::tc_fence_after();
+        int stg = 0, use = 0, acc = 0, ause = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+          trace_stamp(p, 0, t, 0);
+          ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
+          ptx::mbar_wait(b_dzpeer + 8 * stg, use & 1);
+          trace_stamp(p, 0, t, 1);
+          ptx::mbar_wait(b_accempty + 8 * acc, (ause & 1) ^ 1);
+          trace_stamp(p, 0, t, 2);
+          ptx::tc_fence_after();
+          const uint32_t dz = smem_base + DP_DZ + stg * 2 * CH;
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)          // K = 256 output features n: 8 steps in the h = 0 chunk, 8 in the h = 1 chunk
+            ptx::mma_f16_ts_2cta(tAcc + acc * 128, tA + ks * 8, ptx::umma_desc_mn_sw128(dz + (ks >> 3) * CH + (ks & 7) * 2048, CH), idesc, ks != 0);
+          ptx::mma_commit_2cta(b_accfull + 8 * acc, 3);
+          ptx::mma_commit_2cta(b_dzempty + 8 * stg, 3);
+          trace_stamp(p, 0, t, 3);
+          if (++stg == DP_STAGES) { stg = 0; ++use; }
+          if (++acc == DP_ACC) { acc = 0; ++ause; }
+        }
+      }
+    } else {
+      // ============================ peer: forward "my image of stage s has landed" to the leader ============================
+      if (ptx::elect_one()) {
+        const uint32_t remote = ptx::mapa(b_dzpeer, 0);
+        int stg = 0, use = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+          ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
+          ptx::mbar_arrive_cluster(remote + 8 * stg);
+          if (++stg == DP_STAGES) { stg = 0; ++use; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ E2: dH^T tile -> d rowvec(o) (atomics per tile) and d inner (registers) ============================
+    const int q = warp & 3, cg = warp >> 2;
+    const int k = rank * 128 + q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    {
+      // W^T: lane k, n in [64 cg, 64 cg + 64) as 16-bit pairs: columns 32 cg .. 32 cg + 31 of the A operand
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pkw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = cg * 64 + c * 32 + 2 * i;
+          pkw[i] = Pack<T>::pack(__ldg(p.w_f32 + (size_t)n * HD + k), __ldg(p.w_f32 + (size_t)(n + 1) * HD + k));
+        }
+        ptx::tmem_st_32x32b_x16(tA + lane_base + cg * 32 + c * 16, pkw);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster(ptx::mapa(b_wfull, 0));
+    }
+    const float ginv = p.consts[CONST_SCALE + 1];
+    const uint32_t accempty_remote = ptx::mapa(b_accempty, 0);
+    uint4* my_inner = reinterpret_cast<uint4*>(smem_gen + DP_INNER) + threadIdx.x;     // slot i at [i * 512 + thread]: conflict-free
+    uint64_t din2[16];                             // d(inner) sums of this thread's 32 points as (even, odd) pairs
+#pragma unroll
+    for (int i = 0; i < 16; ++i) din2[i] = 0ull;
+    auto load_inner = [&](int64_t jb) {            // this thread's column k of its 32 inner rows, 16-bit
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t j = jb * TILE_M + cg * 32 + c * 8 + i;
+          v[i] = j < p.n_inner ? __ldg(p.inner_f32 + j * HD + k) : 0.f;
+        }
+        my_inner[c * 512] = make_uint4(Pack<T>::pack(v[0], v[1]), Pack<T>::pack(v[2], v[3]), Pack<T>::pack(v[4], v[5]),
+                                       Pack<T>::pack(v[6], v[7]));
+      }
+    };
+    auto flush_din = [&](int64_t jb) {
+      float* dcol = p.d_inner + (jb * TILE_M + cg * 32) * HD + k;       // lanes = consecutive k: coalesced atomics
+#pragma unroll
+      for (int i2 = 0; i2 < 16; ++i2) {
+        float d0, d1;
+        ptx::unpack_f32x2(din2[i2], d0, d1);
+        if (jb * TILE_M + cg * 32 + 2 * i2 < p.n_inner) atomicAdd(dcol + (size_t)(2 * i2) * HD, d0 * ginv);
+        if (jb * TILE_M + cg * 32 + 2 * i2 + 1 < p.n_inner) atomicAdd(dcol + (size_t)(2 * i2 + 1) * HD, d1 * ginv);
+        din2[i2] = 0ull;
+      }
+    };
+    auto load_rv = [&](int o_local) -> uint32_t {  // rowvec(o)[k]: the raw 16-bit value the forward multiplied with
+      if (OP != COORDX_FUSE_PROD) return 0u;
+      return __ldg(reinterpret_cast<const uint16_t*>(p.outer_img) + (size_t)o_local * HD + k);
+    };
+    TileWalk w(runs, n_o);
+    int64_t cur_jb = -1;
+    bool dirty = false;
+    uint32_t rv_next = w.valid ? load_rv(w.o) : 0u;
+    const bool tr = (warp == 0 || warp == 12) && lane == 0;
+    const int trole = warp == 0 ? 1 : 2;
+    int acc = 0, ause = 0;
+    for (int tc = 0; w.valid; ++tc) {
+      const uint32_t rv_raw = rv_next;
+      const int64_t jb = w.jb;
+      const int o_local = w.o;
+      w.advance();
+      if (w.valid) rv_next = load_rv(w.o);                             // in flight during this tile
+      if (jb != cur_jb) {                          // new block of inner rows: the sweep over o is complete
+        if (dirty) flush_din(cur_jb);
+        dirty = false;
+        if (OP == COORDX_FUSE_PROD) load_inner(jb);
+        cur_jb = jb;
+      }
+      if (tr) trace_stamp(p, trole, tc, 0);
+      ptx::mbar_wait(b_accfull + 8 * acc, ause & 1);
+      if (tr) trace_stamp(p, trole, tc, 1);
+      ptx::tc_fence_after();
+      const uint32_t tacc = tAcc + acc * 128 + cg * 32 + lane_base;
+      uint64_t acc2 = 0ull;
+      uint32_t r[2][16];
+      ptx::tmem_ld_32x32b_x16(tacc, r[0]);
+      ptx::tmem_ld_32x32b_x16(tacc + 16, r[1]);
+      uint4 iv[4];
+      if (OP == COORDX_FUSE_PROD) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) iv[c] = my_inner[c * 512];
+      }
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(accempty_remote + 8 * acc);
+      if (tr) trace_stamp(p, trole, tc, 2);
+      const float rv = OP == COORDX_FUSE_PROD ? Pack<T>::unpack(pin_after_waits(rv_raw), 0) : 1.f;
+      const uint64_t rv2 = ptx::pack_f32x2(rv, rv);
+#pragma unroll
+      for (int i2 = 0; i2 < 16; ++i2) {
+        const uint64_t dh2 = ptx::pack_f32x2(__uint_as_float(r[i2 >> 3][2 * (i2 & 7)]), __uint_as_float(r[i2 >> 3][2 * (i2 & 7) + 1]));
+        if (OP == COORDX_FUSE_PROD) {
+          const uint4 v = iv[i2 >> 2];
+          const uint32_t w16 = (i2 & 3) == 0 ? v.x : ((i2 & 3) == 1 ? v.y : ((i2 & 3) == 2 ? v.z : v.w));
+          acc2 = ptx::fma_f32x2(dh2, ptx::pack_f32x2(Pack<T>::unpack(w16, 0), Pack<T>::unpack(w16, 1)), acc2);
+          din2[i2] = ptx::fma_f32x2(rv2, dh2, din2[i2]);
+        } else {
+          acc2 = ptx::add_f32x2(acc2, dh2);
+          din2[i2] = ptx::add_f32x2(din2[i2], dh2);
+        }
+      }
+      float a0, a1;
+      ptx::unpack_f32x2(acc2, a0, a1);
+      atomicAdd(p.d_rv + (int64_t)o_local * HD + k, (a0 + a1) * ginv);
+      if (tr) trace_stamp(p, trole, tc, 3);
+      dirty = true;
+      if (++acc == DP_ACC) { acc = 0; ++ause; }
+    }
+    if (dirty) flush_din(cur_jb);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                             // both CTAs are done with each other's barriers / operands
+  if (warp == W_MMA) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// =================================================================================
 // kernels: the two passes on their own, and both in ONE launch
 // =================================================================================
 template <typename T, int OP, int ACT, int O>
@@ -761,7 +1161,18 @@ trunk_bwd_dw2_kernel(const BwdParams p) {
   const int h = blockIdx.x & 1;                    // half of the trunk's output features
   const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
   const int64_t total = (int64_t)p.nb * (p.o_end - p.o_begin);
-  dw2_body<T, OP, ACT, O>(p, smem_raw, h, TileRuns::single(total * cta / n_cta, total * (cta + 1) / n_cta));
+  dw2_body<T, OP, ACT, O, false>(p, smem_raw, h, TileRuns::single(total * cta / n_cta, total * (cta + 1) / n_cta));
+}
+
+// the dW pass as CTA pairs (see dw2_body, PAIR): blocks 2 i and 2 i + 1 are one cluster
+template <typename T, int OP, int ACT, int O>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW2_THREADS, 1)
+trunk_bwd_dw3_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int h = (int)ptx::cluster_ctarank();
+  const int n_cta = gridDim.x >> 1, cta = blockIdx.x >> 1;
+  const int64_t total = (int64_t)p.nb * (p.o_end - p.o_begin);
+  dw2_body<T, OP, ACT, O, true>(p, smem_raw, h, TileRuns::single(total * cta / n_cta, total * (cta + 1) / n_cta));
 }
 
 template <typename T, int OP>
@@ -798,7 +1209,7 @@ trunk_bwd_fused_kernel(const BwdParams p) {
   const int64_t rb = total * p0 / n_pairs, re = total * p1 / n_pairs;
   const int G = p.fused_chunk < 0 ? -p.fused_chunk : p.fused_chunk;      // (< 0: timing aid, the consumers do nothing)
   if (prod) {
-    dw2_body<T, OP, ACT, O>(p, smem_raw, blockIdx.x & 1, TileRuns::make(rb, re, G, me - p0, p1 - p0));
+    dw2_body<T, OP, ACT, O, false>(p, smem_raw, blockIdx.x & 1, TileRuns::make(rb, re, G, me - p0, p1 - p0));
   } else {
     dfeat_body<T, OP, true>(p, smem_raw, TileRuns::make(rb, c1 > c0 && p.fused_chunk > 0 ? re : rb, G, me - c0, c1 - c0));
   }
@@ -843,12 +1254,27 @@ int launch_bwd_fused(const BwdParams& bp, int precision, int op, int act, int O,
   return launch_fused_t<__half>(bp, op, act, O, grid, st);
 }
 
+// COORDX_BWD_PAIR=1 selects the CTA-pair form of the dW pass (trunk_bwd_dw3_kernel).  Opt-in: it halves the tensor
+// cores' operand fetch and takes the E1 warps' wait for Z^T from ~550 to ~180 clk per sub-tile, but E1 itself - the
+// sin / cos arithmetic plus its tail, ~1.5 k clk per sub-tile - is what bounds the pass, and the pair's producers
+// write two operand layouts per tile: 1024-1035 us against 970 us for the single-CTA form (profiles/r02g_dw_pair.txt).
+static bool dw_pair_wanted() {
+  const char* e = getenv("COORDX_BWD_PAIR");
+  return e && e[0] == '1';
+}
+
 template <typename T, int OP, int ACT, int O>
 static int launch_dw2_inst(const BwdParams& bp, int grid, cudaStream_t st) {
-  static AttrOnce once;
-  auto kern = trunk_bwd_dw2_kernel<T, OP, ACT, O>;
-  CX_TRY(once.set(kern, (int)d2_smem_bytes(O)));
-  kern<<<grid, DW2_THREADS, d2_smem_bytes(O), st>>>(bp);
+  static AttrOnce once, once3;
+  if (dw_pair_wanted()) {
+    auto kern = trunk_bwd_dw3_kernel<T, OP, ACT, O>;
+    CX_TRY(once3.set(kern, (int)d2_smem_bytes(O)));
+    kern<<<grid, DW2_THREADS, d2_smem_bytes(O), st>>>(bp);
+  } else {
+    auto kern = trunk_bwd_dw2_kernel<T, OP, ACT, O>;
+    CX_TRY(once.set(kern, (int)d2_smem_bytes(O)));
+    kern<<<grid, DW2_THREADS, d2_smem_bytes(O), st>>>(bp);
+  }
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -878,12 +1304,24 @@ int launch_dw2(const BwdParams& bp, int precision, int op, int act, int O, int g
   return launch_dw2_t<__half>(bp, op, act, O, grid, st);
 }
 
+// COORDX_BWD_DFEAT_PAIR=0 selects the single-CTA form of the feature-gradient pass (A/B timing)
+static bool dfeat_pair_wanted() {
+  const char* e = getenv("COORDX_BWD_DFEAT_PAIR");
+  return !(e && e[0] == '0');
+}
+
 template <typename T, int OP>
 static int launch_dfeat_inst(const BwdParams& bp, int n_cta, cudaStream_t st) {
-  static AttrOnce once;
-  auto kern = trunk_bwd_dfeat_kernel<T, OP>;
-  CX_TRY(once.set(kern, (int)DF_TOTAL));
-  kern<<<n_cta, DF_THREADS, DF_TOTAL, st>>>(bp);
+  static AttrOnce once, once_pair;
+  if (dfeat_pair_wanted() && n_cta >= 2) {
+    auto kern = trunk_bwd_dfeat_pair_kernel<T, OP>;
+    CX_TRY(once_pair.set(kern, (int)DP_TOTAL));
+    kern<<<n_cta & ~1, DP_THREADS, DP_TOTAL, st>>>(bp);
+  } else {
+    auto kern = trunk_bwd_dfeat_kernel<T, OP>;
+    CX_TRY(once.set(kern, (int)DF_TOTAL));
+    kern<<<n_cta, DF_THREADS, DF_TOTAL, st>>>(bp);
+  }
   CX_LAUNCH_CHECK();
   return 0;
 }

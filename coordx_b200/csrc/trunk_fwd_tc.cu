@@ -142,7 +142,9 @@ constexpr float POLY_MAGIC = 6144.f;
 constexpr float POLY_C0 = 0.99999325f, POLY_C1 = -4.93393467f, POLY_C2 = 4.0412481f, POLY_C3 = -1.22203176f;
 
 __device__ __forceinline__ void trace_stamp(const FwdParams& p, int role, int it, int slot) {
+#if COORDX_TRACE
   if (p.trace != nullptr && blockIdx.x == 0 && it < TRACE_ITERS) p.trace[(role * TRACE_ITERS + it) * 4 + slot] = clock64();
+#endif
 }
 
 template <typename T, int OP, int ACT, int O, int NM>
@@ -636,7 +638,13 @@ static bool g_profile = false;
 static cudaEvent_t g_prof_ev[2] = {nullptr, nullptr};
 static long long* g_trace = nullptr;
 void profile_enable(bool on) { g_profile = on; }
-void profile_set_trace(void* dev_buf) { g_trace = (long long*)dev_buf; }
+int profile_set_trace(void* dev_buf) {
+#if !COORDX_TRACE
+  if (dev_buf) return set_err(COORDX_ERR_UNSUPPORTED, "pipeline tracing is a build option%s (scripts/build_trace_lib.sh, -DCOORDX_TRACE=1)");
+#endif
+  g_trace = (long long*)dev_buf;
+  return 0;
+}
 // milliseconds of the last profiled trunk kernel (synchronises on its end event)
 int profile_last_ms(float* ms_host) {
   if (!ms_host || !g_prof_ev[0]) return set_err(COORDX_ERR_ARG, "no profiled launch%s");

@@ -3,6 +3,8 @@
 epilogue groups and producer warp 8 waited / worked, in SM clocks.  Run on the GPU box."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the stamps are a build option: scripts/build_trace_lib.sh
+os.environ.setdefault('COORDX_B200_LIB', os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'coordx_b200', '_build', 'libcoordx_trace.so'))
 import numpy as np
 import torch
 import __graft_entry__ as G
