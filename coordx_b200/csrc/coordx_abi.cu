@@ -583,6 +583,32 @@ int coordx_loss_forward_backward(int kind, const float* out, const float* gt, in
   return 0;
 }
 
+// coordx_trunk_forward with the loss of training.py:133-135 (loss_functions.py:8-12 image_mse, :56-60 occupancy_3d) fused
+// into the last layer: the tcgen05 trunk evaluates it in its epilogue (the thread that completes out[p, :] reads
+// gt[p, :], writes d loss / d out and keeps a running sum: no pass over [P, O] besides the kernel's own store);
+// every other path (separable sum evaluation, FP32) runs its forward followed by the loss kernel - same results.
+int coordx_trunk_forward_loss(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
+                              int64_t row_end, float* out, int loss_kind, const float* gt, float inv_count,
+                              float* loss_accum, float* dout, int precision, void* ws, size_t ws_bytes, void* stream) {
+  CX_TRY(check_net(net));
+  if (loss_kind != COORDX_LOSS_MSE && loss_kind != COORDX_LOSS_BCE) return set_err(COORDX_ERR_ARG, "unknown loss%s (%lld)", "", loss_kind);
+  if (!feats || !n || !gt || !loss_accum || !dout || !out) return set_err(COORDX_ERR_ARG, "null argument%s");
+  if (row_begin < 0 || row_end > n[0] || row_begin > row_end) return set_err(COORDX_ERR_ARG, "bad slab%s [%lld, %lld)", "", row_begin, row_end);
+  int64_t pts = row_end - row_begin;
+  for (int c = 1; c < net->n_branches; ++c) pts *= n[c];
+  if (pts == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc_path = !(sep::enabled() && sep::supported(net)) && precision != COORDX_PREC_FP32;
+  if (tc_path) {
+    if (!tc::tc_supported(net, precision)) return set_err(COORDX_ERR_UNSUPPORTED, "tcgen05 trunk does not cover this architecture%s");
+    const tc::FwdLoss fl{loss_kind, gt, inv_count, loss_accum, dout};
+    return tc::trunk_forward_tc(net, feats, n, row_begin, row_end, out, precision, ws, ws_bytes, st, &fl);
+  }
+  CX_TRY(coordx_trunk_forward(net, feats, n, row_begin, row_end, out, precision, ws, ws_bytes, stream));
+  const int ow = net->layer_out[net->n_layers - 1];
+  return coordx_loss_forward_backward(loss_kind, out, gt, pts * ow, inv_count, loss_accum, dout, stream);
+}
+
 int coordx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                      float beta1, float beta2, float eps, int64_t step_host, const float* grad_scale_dev, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || step_host < 1) return set_err(COORDX_ERR_ARG, "bad adam argument%s");

@@ -66,8 +66,16 @@ __device__ __forceinline__ uint32_t fuse2(uint32_t x, uint32_t y) {
 // ---- entry points of the two tcgen05 translation units (called from coordx_abi.cu)
 bool tc_supported(const coordx_net* net, int precision);
 size_t fwd_workspace_bytes(int64_t n_inner);
+struct FwdLoss {            // loss fused into the last layer (coordx_trunk_forward_loss)
+  int kind;
+  const float* gt;
+  float inv_count;
+  float* loss_acc;
+  float* dout;
+};
 int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
-                     int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+                     int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st,
+                     const FwdLoss* loss = nullptr);
 void profile_enable(bool on);
 int profile_set_trace(void* dev_buf);
 int profile_set_bwd_trace(void* dev_buf, int pass);

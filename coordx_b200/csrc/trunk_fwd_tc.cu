@@ -105,6 +105,13 @@ struct FwdParams {
   int nb;                   // inner blocks = ceil(n_inner / 128)
   float* out;               // [(o_end - o_begin) * n_inner, O]
   float S;
+  // loss fused into the last layer (LOSS instantiation; training.py:133-135 + loss_functions.py:8-12 / 56-60): the epilogue
+  // thread that completes out[p, :] also reads gt[p, :], writes d loss / d out and keeps a running loss sum
+  const float* gt;          // [same layout as out]
+  float* dout;              // [same layout as out]   d loss / d out, mean reduction (inv_count)
+  float* loss_acc;          // [1] += loss
+  float inv_count;
+  int loss_kind;            // COORDX_LOSS_MSE | COORDX_LOSS_BCE
   long long* trace;         // optional [4 roles][TRACE_ITERS][4] SM-clock stamps written by CTA 0 (profiling hook)
 };
 constexpr int TRACE_ITERS = 96;
@@ -147,7 +154,9 @@ __device__ __forceinline__ void trace_stamp(const FwdParams& p, int role, int it
 #endif
 }
 
-template <typename T, int OP, int ACT, int O, int NM>
+// LOSS: 0 = plain forward, 1 + COORDX_LOSS_* = that loss fused into the last layer (a compile-time kind: with the
+// kind as a run-time branch the unused BCE code alone cost the 2048^2 step 13-26 us)
+template <typename T, int OP, int ACT, int O, int NM, int LOSS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 trunk_fwd_tc_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -382,6 +391,8 @@ trunk_fwd_tc_kernel(const FwdParams p) {
     // (alternating the storer role balanced the groups, put them back in phase and was 9 % slower).  Slot reuse
     // distance 4 >> the <= 1.25-tile skew the accumulator hand-off allows between any two epilogue warps.
     float pend[O];                               // group 0: own partial sums of the previous tile
+    float pend_gt[O];                            // LOSS: the targets of that row, loaded when the row was parked
+    float loss_part = 0.f;                       // LOSS: this thread's running loss sum
     float* pend_dst = nullptr;
     int pend_it = -1;
     auto finalize = [&]() {
@@ -390,7 +401,26 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         if (pend_dst != nullptr) {
           const float* xb = xch + (pend_it & (XCH_DEPTH - 1)) * (MAX_O * TILE_M);
 #pragma unroll
-          for (int oo = 0; oo < O; ++oo) pend_dst[oo] = pend[oo] + xb[oo * TILE_M + row] + c_epi.bf[oo];
+          for (int oo = 0; oo < O; ++oo) {
+            const float x = pend[oo] + xb[oo * TILE_M + row] + c_epi.bf[oo];
+            pend_dst[oo] = x;
+            if (LOSS) {                          // same expressions as loss_kernel (elementwise.cuh)
+              const float z = pend_gt[oo];
+              float l, d;
+              if (LOSS == 1 + COORDX_LOSS_MSE) {
+                const float e = x - z;
+                l = e * e;
+                d = 2.f * e;
+              } else {
+                const float ex = expf(-fabsf(x));
+                l = fmaxf(x, 0.f) - x * z + logf(1.f + ex);
+                const float sig = x >= 0.f ? 1.f / (1.f + ex) : ex / (1.f + ex);
+                d = sig - z;
+              }
+              loss_part += l;
+              p.dout[(pend_dst - p.out) + oo] = d * p.inv_count;
+            }
+          }
         }
       }
     };
@@ -521,6 +551,10 @@ trunk_fwd_tc_kernel(const FwdParams p) {
         pend_it = it;
 #pragma unroll
         for (int oo = 0; oo < O; ++oo) pend[oo] = acc[oo];
+        if (LOSS && pend_dst != nullptr) {
+#pragma unroll
+          for (int oo = 0; oo < O; ++oo) pend_gt[oo] = __ldg(p.gt + (pend_dst - p.out) + oo);
+        }
       }
       if (q == 0 && lane == 0) trace_stamp(p, 1 + E, it, 3);
       t_cur += 2;
@@ -528,6 +562,11 @@ trunk_fwd_tc_kernel(const FwdParams p) {
       while (ol_e >= n_o32) { ol_e -= n_o32; ++jb_e; }
     }
     finalize();                                  // the last tile
+    if (LOSS && E == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+      if (lane == 0) atomicAdd(p.loss_acc, loss_part * p.inv_count);
+    }
     };
     if (e == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
   }
@@ -553,10 +592,21 @@ template <> struct MufuCols<__nv_bfloat16> { static constexpr int value = COORDX
 
 template <typename T, int OP, int ACT, int O>
 static int launch_fwd_inst(const FwdParams& fp, int grid, cudaStream_t st) {
-  auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, (ACT == COORDX_ACT_SINE ? MufuCols<T>::value : 32)>;
-  static AttrOnce once;
-  CX_TRY(once.set(kern, (int)SMEM_ALLOC));
-  kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);
+  constexpr int NM = ACT == COORDX_ACT_SINE ? MufuCols<T>::value : 32;
+  static AttrOnce once, once_mse, once_bce;
+  if (fp.gt != nullptr && fp.loss_kind == COORDX_LOSS_MSE) {
+    auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, NM, 1 + COORDX_LOSS_MSE>;
+    CX_TRY(once_mse.set(kern, (int)SMEM_ALLOC));
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);
+  } else if (fp.gt != nullptr) {
+    auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, NM, 1 + COORDX_LOSS_BCE>;
+    CX_TRY(once_bce.set(kern, (int)SMEM_ALLOC));
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);
+  } else {
+    auto kern = trunk_fwd_tc_kernel<T, OP, ACT, O, NM, 0>;
+    CX_TRY(once.set(kern, (int)SMEM_ALLOC));
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, st>>>(fp);
+  }
   CX_LAUNCH_CHECK();
   return 0;
 }
@@ -668,7 +718,8 @@ static unsigned g_next_copy = 0;
 
 // feats: C tables [n_c, 256] fp32.  The last axis is the inner axis; axes 0..C-2 are outer.
 int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t row_begin,
-                     int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st) {
+                     int64_t row_end, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st,
+                     const FwdLoss* loss) {
   const int C = net->n_branches;
   const int L = net->n_pre;                       // trunk = layers L (Hd x Hd) and L+1 (Hd -> O)
   const int O = net->layer_out[L + 1];
@@ -691,6 +742,9 @@ int trunk_forward_tc(const coordx_net* net, const float* const* feats, const int
   fp.out = out;
   fp.S = S;
   fp.trace = g_trace;
+  if (loss != nullptr) {
+    fp.gt = loss->gt; fp.dout = loss->dout; fp.loss_acc = loss->loss_acc; fp.inv_count = loss->inv_count; fp.loss_kind = loss->kind;
+  }
   const int64_t total = (int64_t)pl.nb * (fp.o_end - fp.o_begin);
   if (total <= 0) return 0;
   const int grid = 2 * (int)min((int64_t)(num_sms() / 2), cdiv(total, 2));

@@ -288,12 +288,44 @@ def _fusion_forward(block, precision, feats, params):
     out = torch.empty(P, block.out_width, dtype=torch.float32, device=dev)
     n_arr = _lib.i64_array(ns)
     f_arr = _lib.ptr_array([f.data_ptr() for f in feats])
+    # SingleBVPNet.forward_with_loss parks (kind, gt) here: the trunk call then also evaluates the loss of the training
+    # step (coordx_trunk_forward_loss; in the tcgen05 kernel's epilogue) and leaves its value and d loss / d out behind
+    hook = getattr(block, '_loss_hook', None)
+    if hook is not None and (hook.get('loss') is not None or hook['gt'].numel() != out.numel()):
+        hook = None                                  # already served by an earlier trunk call / not this grid
     with torch.cuda.device(dev):
         ws_bytes = lib.coordx_trunk_workspace_bytes(desc.net, n_arr, 0, ns[0], prec, 0)
         ws = _workspace(ws_bytes, dev)
-        _lib.check(lib.coordx_trunk_forward(desc.net, f_arr, n_arr, 0, ns[0], out.data_ptr(), prec, ws.data_ptr(),
-                                            ws.numel(), _stream_ptr()), 'coordx_trunk_forward')
+        if hook is None:
+            _lib.check(lib.coordx_trunk_forward(desc.net, f_arr, n_arr, 0, ns[0], out.data_ptr(), prec, ws.data_ptr(),
+                                                ws.numel(), _stream_ptr()), 'coordx_trunk_forward')
+        else:
+            gt = _as_f32c(hook['gt'].reshape(P, block.out_width))
+            loss = torch.zeros((), dtype=torch.float32, device=dev)
+            dout = torch.empty_like(out)
+            _lib.check(lib.coordx_trunk_forward_loss(desc.net, f_arr, n_arr, 0, ns[0], out.data_ptr(), hook['kind'],
+                                                     gt.data_ptr(), 1.0 / max(out.numel(), 1), loss.data_ptr(),
+                                                     dout.data_ptr(), prec, ws.data_ptr(), ws.numel(), _stream_ptr()),
+                       'coordx_trunk_forward_loss')
+            hook['loss'], hook['dout'] = loss, dout
     return out, feats, prec
+
+
+class _TrunkLossFn(torch.autograd.Function):
+    """The loss value the trunk call has already produced (coordx_trunk_forward_loss), attached to `out` in the
+    autograd graph: its backward hands the saved d loss / d out to the trunk's backward.  unit_grad: the caller
+    promises an upstream gradient of exactly 1 (`loss.backward()` on this scalar), see loss_functions.fused_loss."""
+
+    @staticmethod
+    def forward(ctx, out, loss, dout, unit_grad):
+        ctx.dout, ctx.shape, ctx.unit_grad = dout, out.shape, unit_grad
+        return loss.detach()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        d = ctx.dout.reshape(ctx.shape)
+        return (d if ctx.unit_grad else d * g), None, None, None
 
 
 def _needs_grad(tensors):
@@ -897,6 +929,32 @@ class SingleBVPNet(nn.Module):
                 coords = [self.positional_encoding(c, single_channel=True) for c in coords]
             output = self.net(coords, split_coord=True, ret_feat=ret_feat)
         return {'model_in': coords_org, 'model_out': output}
+
+    def forward_with_loss(self, model_input, gt, loss='mse', unit_grad=False):
+        """forward() and the loss of the training step (training.py:112,133-135) in ONE call - an addition to the
+        reference API: returns (model_output_dict, loss scalar).  loss: 'mse' = image_mse without mask
+        (loss_functions.py:8-12), 'bce' = occupancy_3d (:56-60); gt: [1, P, O].  On the split grid path the loss is
+        fused into the trunk's last layer (coordx_trunk_forward_loss: evaluated in the tcgen05 kernel's epilogue
+        together with d loss / d model_out, no separate pass over the output); everything else takes forward()
+        followed by loss_functions.fused_loss, with identical results."""
+        from .loss_functions import fused_loss
+        if loss not in ('mse', 'bce'):
+            raise ValueError(f'unknown loss {loss!r}')
+        hook = None
+        if self.split_mlp and 'coords_split' in model_input and 'coords' not in model_input and gt.is_cuda:
+            hook = {'kind': _lib.LOSS_MSE if loss == 'mse' else _lib.LOSS_BCE, 'gt': gt.detach(), 'loss': None, 'dout': None}
+            self.net._loss_hook = hook
+        try:
+            output = self.forward(model_input)
+        finally:
+            if hook is not None:
+                self.net._loss_hook = None
+        out = output['model_out']
+        if hook is not None and hook['loss'] is not None:
+            value = _TrunkLossFn.apply(out, hook['loss'], hook['dout'], unit_grad) if out.requires_grad else hook['loss']
+        else:
+            value = fused_loss(loss, out, gt, unit_grad=unit_grad)
+        return output, value
 
     def forward_split_channel(self, coord, channel_id):
         """modules.py:463-470"""

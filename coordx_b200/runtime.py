@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
+import os
+
 import torch
 
 from . import _lib
@@ -193,6 +195,8 @@ class CapturedTrainStep:
                 raise ValueError('CapturedTrainStep needs an optimizer constructed with capturable=True')
             self.opt = optimizer
             self._own_opt = False
+        # COORDX_FUSED_LOSS=0: forward + separate loss kernel (A/B timing of the loss fused into the trunk)
+        self.loss_kind = loss if loss in ('mse', 'bce') and os.environ.get('COORDX_FUSED_LOSS', '1') != '0' else None
         if callable(loss):
             self.loss_fn = loss
         elif loss in ('mse', 'bce'):                 # one kernel: value and d loss / d out (loss_functions.py)
@@ -232,8 +236,13 @@ class CapturedTrainStep:
         torch.cuda.synchronize()
 
     def _iteration(self):
-        out = self.model({'coords_split': self.static_coords})['model_out']
-        loss = self.loss_fn(out, self.static_gt)
+        if self.loss_kind is not None and hasattr(self.model, 'forward_with_loss'):
+            # loss fused into the trunk's last layer (coordx_trunk_forward_loss)
+            _, loss = self.model.forward_with_loss({'coords_split': self.static_coords}, self.static_gt, self.loss_kind,
+                                                   unit_grad=True)
+        else:
+            out = self.model({'coords_split': self.static_coords})['model_out']
+            loss = self.loss_fn(out, self.static_gt)
         loss.backward()
         if self.world > 1:
             from . import sharding

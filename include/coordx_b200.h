@@ -135,6 +135,15 @@ size_t coordx_trunk_workspace_bytes(const coordx_net* net, const int64_t* n, int
 int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const int64_t* n,
                          int64_t row_begin, int64_t row_end, float* out, int precision,
                          void* ws, size_t ws_bytes, void* stream);
+/* The same forward with the loss of the training step fused into the last layer (training.py:133-135 calls
+ * loss_fn(model_output, gt) on the [1, P, O] result: loss_functions.py:8-12 image_mse = COORDX_LOSS_MSE,
+ * :56-60 occupancy_3d = COORDX_LOSS_BCE; mean reduction, inv_count = 1 / (P * O) of the grid the mean runs over).
+ * gt, dout: [slab points, out_width] like out.  loss_accum[0] += loss of the slab, dout = d loss / d out.
+ * On the tcgen05 path the loss is evaluated in the trunk kernel's epilogue (no extra pass over [P, O]).      */
+int coordx_trunk_forward_loss(const coordx_net* net, const float* const* feats, const int64_t* n,
+                              int64_t row_begin, int64_t row_end, float* out, int loss_kind, const float* gt,
+                              float inv_count, float* loss_accum, float* dout, int precision,
+                              void* ws, size_t ws_bytes, void* stream);
 /* dout [slab points, out_width] -> trunk weight grads + dfeat[c] [n[c], fuse_width]
  * (accumulated; dfeat of axis 0 only touches rows [row_begin,row_end)).                  */
 int coordx_trunk_backward(const coordx_net* net, const float* const* feats, const int64_t* n,
