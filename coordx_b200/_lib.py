@@ -127,7 +127,7 @@ def load():
             fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.coordx_abi_version() != 2:
+        if lib.coordx_abi_version() != 3:
             raise CoordxError('libcoordx_b200.so ABI version mismatch')
         _lib = lib
     return _lib

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define COORDX_ABI_VERSION 2
+#define COORDX_ABI_VERSION 3
 #define COORDX_MAX_BRANCHES 4
 #define COORDX_MAX_LAYERS 12
 
