@@ -61,6 +61,7 @@ struct BwdParams {
   int fused_pairs;           // fused kernel: number of dW CTA pairs (the other CTAs of the grid run the feature-gradient pass)
   int fused_chunk;           // fused kernel: tiles per hand-over chunk
   int fused_groups;          // fused kernel: groups of CTAs that sweep a range of tiles together
+  int dz_no_wf;              // the stored dZ^T tiles lack the factor wfs[0][n] (dz_without_wf): the feature-gradient pass folds it into W^T
 };
 
 // consts[] layout (floats): [256] bias' | [MAX_O][256] wfs | loss scale, 1 / loss scale, max|dout| bits, pad
@@ -94,6 +95,14 @@ __device__ __forceinline__ void load_rowvec8(const BwdParams& p, int64_t o, int 
     }
   }
 }
+
+// One output (O = 1), sine, bf16 operands: dZ[p, n] = dout[p] * wfs[n] * cos(..) is stored and fed to the GEMMs WITHOUT
+// its per-feature factor wfs[n] = S Wf[n] - one packed multiply less per pair in E1, the loop that bounds the dW pass.
+// The factor comes back for free: dW_h and db are scaled per row when they are flushed, and the feature-gradient pass
+// multiplies it into its W^T operand when it loads it (dH = dZ W = dZ' (diag(wfs) W)).  fp16 operands keep the factor
+// (their power-of-two loss scale rides on wfs).
+template <typename T>
+__host__ __device__ constexpr bool dz_without_wf(int act, int O) { return act == COORDX_ACT_SINE && O == 1 && Pack<T>::kFmt == 1; }
 
 // ---- entry points of trunk_bwd_tc2.cu
 int launch_dw2(const BwdParams& bp, int precision, int op, int act, int O, int grid, cudaStream_t st);

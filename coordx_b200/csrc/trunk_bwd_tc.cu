@@ -98,6 +98,17 @@ prep_bwd_consts_kernel(const float* __restrict__ b, const float* __restrict__ Wf
   if (i < MAX_O * HD) consts[HD + i] = (i >> 8) < O ? sc * Wf[i] : 0.f;
 }
 
+// the same constants plus a unit loss scale in ONE launch (bf16 operands: no scale needed, see prep_scale_kernel)
+__global__ void __launch_bounds__(256)
+prep_bwd_consts_unit_kernel(const float* __restrict__ b, const float* __restrict__ Wf, int O, int act, float S, float* __restrict__ consts) {
+  const float sc = act == COORDX_ACT_SINE ? S : 1.f;
+  for (int i = threadIdx.x; i < MAX_O * HD; i += 256) {
+    if (i < HD) consts[i] = sc * b[i];
+    consts[HD + i] = (i >> 8) < O ? sc * Wf[i] : 0.f;
+  }
+  if (threadIdx.x < 2) consts[CONST_SCALE + threadIdx.x] = 1.f;
+}
+
 // max |x| over a tensor, as the bit pattern of a non-negative float (atomicMax on unsigned keeps the order)
 __global__ void __launch_bounds__(256)
 absmax_kernel(const float* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
@@ -1495,26 +1506,36 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
   const int64_t n1 = C == 3 ? n[1] : 1;
   const int64_t n_last = n[C - 1];
 
-  prep_weights_kernel<T><<<HD * HD / 256, 256, 0, st>>>(net->layer_w[L], net->layer_b[L], net->layer_w[L + 1], net->layer_b[L + 1],
-                                                       O, net->act, S, w_img, nullptr);
-  CX_LAUNCH_CHECK();
-  prep_bwd_consts_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], O, net->act, S, consts);
-  CX_LAUNCH_CHECK();
   const bool v1 = bwd_v1();
+  // the 16-bit weight / inner-block images feed the first-generation and the recompute kernels only: the stored-dZ path
+  // (dw2 + dfeat) converts the fp32 tables itself
+  const bool need_images = v1 || !pl.reuse;
+  if (need_images) {
+    prep_weights_kernel<T><<<HD * HD / 256, 256, 0, st>>>(net->layer_w[L], net->layer_b[L], net->layer_w[L + 1], net->layer_b[L + 1],
+                                                         O, net->act, S, w_img, nullptr);
+    CX_LAUNCH_CHECK();
+  }
   const bool fp16 = sizeof(T) == 2 && Pack<T>::kFmt == 0;
   const int64_t n_pts = (r1 - r0) * n1 * n_last;
   if (fp16 && !v1) {                               // max|dout| for the loss scale (bf16 needs none)
+    prep_bwd_consts_kernel<<<MAX_O * HD / 256, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], O, net->act, S, consts);
+    CX_LAUNCH_CHECK();
     CX_CUDA(cudaMemsetAsync(consts + CONST_SCALE + 2, 0, 4, st));
     absmax_kernel<<<(unsigned)min(cdiv(n_pts * O, 256 * 8), (int64_t)(4 * num_sms())), 256, 0, st>>>(dout, n_pts * O,
                                                                                                (unsigned*)(consts + CONST_SCALE + 2));
     CX_LAUNCH_CHECK();
+    prep_scale_kernel<<<1, 256, 0, st>>>(consts, O, 1);
+    CX_LAUNCH_CHECK();
+  } else {
+    prep_bwd_consts_unit_kernel<<<1, 256, 0, st>>>(net->layer_b[L], net->layer_w[L + 1], O, net->act, S, consts);
+    CX_LAUNCH_CHECK();
   }
-  prep_scale_kernel<<<1, 256, 0, st>>>(consts, O, fp16 && !v1 ? 1 : 0);
-  CX_LAUNCH_CHECK();
   // ---------------- pass W: tiles = (outer index, 128 rows of the last axis): dW, db, dWf
   // ---------------- pass A: same tiles: d(outer features)
-  prep_inner_kernel<T><<<(unsigned)cdiv((int64_t)pl.nbA * TILE_M * HD, 256), 256, 0, st>>>(feats[C - 1], n_last, innerA, (int64_t)pl.nbA * TILE_M);
-  CX_LAUNCH_CHECK();
+  if (need_images) {
+    prep_inner_kernel<T><<<(unsigned)cdiv((int64_t)pl.nbA * TILE_M * HD, 256), 256, 0, st>>>(feats[C - 1], n_last, innerA, (int64_t)pl.nbA * TILE_M);
+    CX_LAUNCH_CHECK();
+  }
   BwdParams a{};
   a.w_img = w_img; a.inner_img = innerA; a.inner_f32 = feats[C - 1]; a.w_f32 = net->layer_w[L]; a.consts = consts;
   a.outer0 = feats[0]; a.outer1 = C == 3 ? feats[1] : nullptr; a.n_outer1 = n1;
@@ -1541,6 +1562,7 @@ static int trunk_backward_tc_t(const coordx_net* net, const float* const* feats,
                                                                                 net->fusion_op, base + pl.rows_off);
       CX_LAUNCH_CHECK();
       a.outer_img = base + pl.rows_off;
+      a.dz_no_wf = dz_without_wf<T>(net->act, O) ? 1 : 0;     // what the dW pass stores (and the dfeat / fused kernels expect)
       if (pl.reuse && bwd_fused_wanted(total)) {
         // ---------------- dW pass and feature-gradient pass side by side in one launch
         const int sms = num_sms();

@@ -19,6 +19,8 @@
 // (d inner) is a per-thread accumulator per point that lives in registers while the CTA sweeps o for a fixed block
 // of inner rows.  W^T is a TMEM-resident A operand (256 columns), so the tensor core fetches only the streamed dZ^T
 // tile from shared memory.
+#include <type_traits>
+
 #include "trunk_bwd_common.cuh"
 
 namespace coordx {
@@ -101,7 +103,7 @@ constexpr uint32_t D2_DOUT = D2_BAR + 256;                 // dout staging: D st
 constexpr int DW2_THREADS = 28 * 32;
 // tuning knobs (A/B builds: scripts/build_variant_bwd2.sh)
 #ifndef COORDX_DW2_NPOLY
-#define COORDX_DW2_NPOLY 2          // of the 8 (even, odd) pairs of a thread's 16 values, how many take the FMA-pipe polynomial
+#define COORDX_DW2_NPOLY 0          // of the 8 (even, odd) pairs of a thread's 16 values, how many take the FMA-pipe polynomial
 #endif
 constexpr int D2_E1_ARRIVALS = 16;      // one elected arrive per E1 warp
 // CTA-pair form: how the leader learns that the PEER's producers / E1 warps are done with a (sub-)tile.
@@ -139,6 +141,9 @@ struct Bars2 {
 // COORDX_DW2_NPOLY of every 8 pairs: scripts/micro/micro_e1.cu times this arithmetic alone (profiles/r02b_micro_e1.txt:
 // 1062 clk per 16 values x 4 warps with 0 / 8, 870 with 2 / 8, 919 with 4 / 8, 1181 with 8 / 8 - MUFU-bound below 2,
 // issue-bound above; scalar FFMAs with immediate coefficients instead of the packed ones are 10 % slower).
+// Inside the kernel the balance moved once the pipeline-trace stamps were compiled out (they sat in this loop): the pass
+// takes 901 us with 0 / 8, 904 with 1 / 8, 922 with 2 / 8, 957 with 4 / 8 (profiles/r02l_poly_share_ab.txt), so the
+// default share is now 0 - the polynomial path stays for the A/B.
 __device__ __forceinline__ uint64_t f2x(float v) { return ptx::pack_f32x2(v, v); }
 __device__ __forceinline__ void sincos_rev_x2(uint64_t t2, uint64_t& sn, uint64_t& cs) {
   const uint64_t m2 = ptx::add_f32x2(t2, f2x(12582912.f));            // 1.5 * 2^23: rounds t to the nearest integer
@@ -484,7 +489,9 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
     float wfs_n[O];                                               // sine: S Wf[o][n]; relu: Wf[o][n]   (times the loss scale)
 #pragma unroll
     for (int oo = 0; oo < O; ++oo) wfs_n[oo] = p.consts[HD + oo * HD + h * 128 + row] * gscale;
-    constexpr bool PACKED = ACT == COORDX_ACT_SINE && O == 1;     // the headline case: packed fp32x2 arithmetic, half the elements off the MUFU
+    constexpr bool PACKED = ACT == COORDX_ACT_SINE && O == 1;     // the headline case: packed fp32x2 arithmetic
+    constexpr bool NOWF = dz_without_wf<T>(ACT, O);               // dZ^T without its factor wfs[n] (trunk_bwd_common.cuh)
+    static_assert(!NOWF || PACKED, "dz_without_wf implies the packed path");
     float db_acc = 0.f;
     float dwf_acc[O];
 #pragma unroll
@@ -496,16 +503,20 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
     int dsg = 0, dsuse = 0;
     const bool tr = q == 0 && lane == 0 && (pq == 0 || pq == 3);
     const int trole = pq == 0 ? 1 : 2;
-    for (int s = 0; s < n_sub; ++s) {
-      const int hh = s & 1;
-      const uint32_t zb = s & 1;
+    const uint32_t zaddr0 = tZ + pq * 16 + lane_base;
+    const uint32_t img_a0 = smem_base + D2_IMG + ptx::sw128_offset(row, pq * 16);
+    // one sub-tile; the half hh (= Z^T buffer = image chunk) is a compile-time constant so that the tensor-memory,
+    // image and barrier addresses are loop invariants (as run-time values they were ~25 of the loop's ~170 instructions)
+    auto e1_sub = [&](auto HHC, const int s) {
+      constexpr int hh = decltype(HHC)::value;
+      constexpr uint32_t zb = hh;
       if (tr) trace_stamp(p, trole, s, 0);
       if (hh == 0) ptx::mbar_wait(B.dsfull + 8 * dsg, dsuse & 1);
       ptx::mbar_wait(B.zfull + 8 * zb, (s >> 1) & 1);
       if (tr) trace_stamp(p, trole, s, 1);
       ptx::tc_fence_after();
       const float* ds = reinterpret_cast<const float*>(smem_gen + D2_DOUT) + (dsg * TILE_M + hh * 64 + pq * 16) * O;
-      const uint32_t zaddr = tZ + zb * 64 + pq * 16 + lane_base;
+      const uint32_t zaddr = zaddr0 + zb * 64;
       uint32_t pk[8];
       uint32_t r[16];
       ptx::tmem_ld_32x32b_x16(zaddr, r);
@@ -530,7 +541,7 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
             sn = ptx::pack_f32x2(__sinf(th0), __sinf(th1));
             cs = ptx::pack_f32x2(__cosf(th0), __cosf(th1));
           }
-          const uint64_t dz = ptx::mul_f32x2(ptx::mul_f32x2(d2[e2], W2), cs);
+          const uint64_t dz = NOWF ? ptx::mul_f32x2(d2[e2], cs) : ptx::mul_f32x2(ptx::mul_f32x2(d2[e2], W2), cs);
           db2 = ptx::add_f32x2(db2, dz);
           dwf2 = ptx::fma_f32x2(d2[e2], sn, dwf2);
           float dz0, dz1;
@@ -579,11 +590,9 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
       ptx::tmem_st_32x32b_x8(zaddr, pk);
       if (p.dz_img) {                              // the image for the dfeat pass: shared memory, then one bulk store per sub-tile
         ptx::mbar_wait(B.imgempty + 8 * zb, ((s >> 1) & 1) ^ 1);
-        uint8_t* dzrow = smem_gen + D2_IMG + zb * CH;
-#pragma unroll
-        for (int pc = 0; pc < 2; ++pc)             // 8 points = one swizzled 16-byte piece of row n
-          *reinterpret_cast<uint4*>(dzrow + ptx::sw128_offset(row, (pq * 2 + pc) * 8)) =
-              make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+        // 2 x 8 points = two swizzled 16-byte pieces of row n (piece index 2 pq and 2 pq + 1: the addresses differ in bit 4)
+        ptx::sts128(img_a0 + zb * CH, pk[0], pk[1], pk[2], pk[3]);
+        ptx::sts128((img_a0 ^ 16u) + zb * CH, pk[4], pk[5], pk[6], pk[7]);
         ptx::fence_proxy_async();
       }
       ptx::tmem_st_wait();
@@ -594,6 +603,10 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
         if (PAIR && !D3_FWD) ptx::mbar_arrive_cluster(ptx::mapa(B.dzpair, 0) + 8 * zb);
       }
       if (tr) trace_stamp(p, trole, s, 3);
+    };
+    for (int t = 0; t < my_tiles; ++t) {
+      e1_sub(std::integral_constant<int, 0>{}, 2 * t);
+      e1_sub(std::integral_constant<int, 1>{}, 2 * t + 1);
     }
     if (my_tiles > 0) {
       if (PACKED) {
@@ -603,7 +616,8 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
         ptx::unpack_f32x2(dwf2, a0, a1);
         dwf_acc[0] = a0 + a1;
       }
-      atomicAdd(p.db + h * 128 + row, db_acc * ginv);
+      const float rscale = NOWF ? ginv * wfs_n[0] : ginv;         // (NOWF: the row factor the tiles were stored without)
+      atomicAdd(p.db + h * 128 + row, db_acc * rscale);
 #pragma unroll
       for (int oo = 0; oo < O; ++oo) atomicAdd(p.dWf + oo * HD + h * 128 + row, dwf_acc[oo]);
       // ---- flush dW_h (accumulated over every tile of this CTA) with one atomic per element
@@ -616,7 +630,7 @@ __device__ __forceinline__ void dw2_body(const BwdParams& p, uint8_t* smem_raw, 
         ptx::tmem_ld_32x32b_x16(tDW + lane_base + pq * 64 + b * 16, rr);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(drow + b * 16 + i, __uint_as_float(rr[i]) * ginv);
+        for (int i = 0; i < 16; ++i) atomicAdd(drow + b * 16 + i, __uint_as_float(rr[i]) * rscale);
       }
     }
   }
@@ -777,7 +791,8 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int n = g * 128 + c * 32 + 2 * i;
-          pkw[i] = Pack<T>::pack(__ldg(p.w_f32 + (size_t)n * HD + k), __ldg(p.w_f32 + (size_t)(n + 1) * HD + k));
+          const float f0 = p.dz_no_wf ? p.consts[HD + n] : 1.f, f1 = p.dz_no_wf ? p.consts[HD + n + 1] : 1.f;
+          pkw[i] = Pack<T>::pack(f0 * __ldg(p.w_f32 + (size_t)n * HD + k), f1 * __ldg(p.w_f32 + (size_t)(n + 1) * HD + k));
         }
         ptx::tmem_st_32x32b_x16(tA + lane_base + blk * 128 + g * 64 + c * 16, pkw);
       }
@@ -1037,7 +1052,8 @@ trunk_bwd_dfeat_pair_kernel(const BwdParams p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int n = cg * 64 + c * 32 + 2 * i;
-          pkw[i] = Pack<T>::pack(__ldg(p.w_f32 + (size_t)n * HD + k), __ldg(p.w_f32 + (size_t)(n + 1) * HD + k));
+          const float f0 = p.dz_no_wf ? p.consts[HD + n] : 1.f, f1 = p.dz_no_wf ? p.consts[HD + n + 1] : 1.f;
+          pkw[i] = Pack<T>::pack(f0 * __ldg(p.w_f32 + (size_t)n * HD + k), f1 * __ldg(p.w_f32 + (size_t)(n + 1) * HD + k));
         }
         ptx::tmem_st_32x32b_x16(tA + lane_base + cg * 32 + c * 16, pkw);
       }
