@@ -924,6 +924,10 @@ __device__ __forceinline__ void dfeat_body(const BwdParams& p, uint8_t* smem_raw
 // whole tile) x K16 (n) per step, A = this CTA's half of W^T in its tensor memory (128 columns), B = dZ^T with each
 // CTA supplying ONE 64-point sub-tile image (so a CTA also loads only half of every tile from HBM).  Operand fetch per
 // SM: 2 KB per 64 clk.  The accumulator of a tile is [128 k x 128 points] = 128 columns: three of them rotate.
+#ifndef COORDX_DP_AHEAD
+#define COORDX_DP_AHEAD 3           // tiles the MMA issue may run ahead of completed tiles (3 = unlimited: one per accumulator;
+                                    // measured per 2048^2: 3: 382.5 us, 2: 380.7 us, 1: 453 us - the queued tiles hold ring stages)
+#endif
 constexpr int DP_STAGES = 6;                               // ring of sub-tile images (2 x 16 KB: both halves of n)
 constexpr int DP_ACC = 3;
 constexpr uint32_t DP_DZ = 0;
@@ -1009,6 +1013,12 @@ trunk_bwd_dfeat_pair_kernel(const BwdParams p) {
         int stg = 0, use = 0, acc = 0, ause = 0;
         for (int t = 0; t < my_tiles; ++t) {
           trace_stamp(p, 0, t, 0);
+          if (COORDX_DP_AHEAD < DP_ACC && t >= COORDX_DP_AHEAD) {
+            // do not run more than COORDX_DP_AHEAD tiles ahead of the tensor pipe: every queued tile holds its stage of the
+            // ring, i.e. costs the loader a stage of prefetch depth
+            const int td = t - COORDX_DP_AHEAD;    // tile whose completion is awaited: accumulator td % 3, its use td / 3
+            ptx::mbar_wait(b_accfull + 8 * (td % DP_ACC), (td / DP_ACC) & 1);
+          }
           ptx::mbar_wait(b_dzfull + 8 * stg, use & 1);
           ptx::mbar_wait(b_dzpeer + 8 * stg, use & 1);
           trace_stamp(p, 0, t, 1);
