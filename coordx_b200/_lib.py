@@ -86,6 +86,7 @@ SIGNATURES = {
     'coordx_trunk_workspace_bytes': (C.c_size_t, [C.POINTER(Net), _I64P, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     'coordx_trunk_forward': (C.c_int, [C.POINTER(Net), _PP, _I64P, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
+    'coordx_gather_rows': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'coordx_trunk_forward_loss': (C.c_int, [C.POINTER(Net), _PP, _I64P, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     'coordx_trunk_backward': (C.c_int, [C.POINTER(Net), _PP, _I64P, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(Grads),

@@ -609,6 +609,19 @@ int coordx_trunk_forward_loss(const coordx_net* net, const float* const* feats, 
   return coordx_loss_forward_backward(loss_kind, out, gt, pts * ow, inv_count, loss_accum, dout, stream);
 }
 
+// ground-truth gather of a training batch (dataio.py:575-600), device-resident data; see gather_rows_kernel
+int coordx_gather_rows(const float* data, int width, const int64_t* idz, int64_t nz, int64_t stride_z, const int64_t* idx,
+                       int64_t m, float* out, void* stream) {
+  if (!data || !idx || !out || width < 1 || nz < 0 || m < 0 || (idz && stride_z < 0)) return set_err(COORDX_ERR_ARG, "bad gather argument%s");
+  if (!idz) nz = 1;
+  const int64_t total = nz * m * width;
+  if (total == 0) return 0;
+  const int blocks = (int)min((int64_t)148 * 16, cdiv(total, 256));
+  gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(data, width, idz, nz, stride_z, idx, m, out);
+  CX_LAUNCH_CHECK();
+  return 0;
+}
+
 int coordx_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                      float beta1, float beta2, float eps, int64_t step_host, const float* grad_scale_dev, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || step_host < 1) return set_err(COORDX_ERR_ARG, "bad adam argument%s");

@@ -131,6 +131,23 @@ loss_kernel(int kind, const float* __restrict__ out, const float* __restrict__ g
   }
 }
 
+// Batch producer of the video / volume path (dataio.py:575-600, Implicit3DWrapper.__getitem__): the reference gathers the
+// ground truth of a training batch on the CPU, data[coord_idx[:, None] * n_xy + coord_idy[None, :]], from a [T * H * W, C]
+// array (943 MB for the 300 x 512 x 512 RGB video) and ships it to the GPU every iteration.  Here the array lives on the
+// device: out[(i * m + j), :] = data[idz[i] * stride_z + idx[j], :]   (idz == nullptr: one level, row idx[j]).
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ data, int width, const int64_t* __restrict__ idz, int64_t nz, int64_t stride_z,
+                   const int64_t* __restrict__ idx, int64_t m, float* __restrict__ out) {
+  const int64_t total = nz * m * width;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / width;
+    const int c = (int)(e - row * width);
+    const int64_t i = row / m, j = row - i * m;
+    const int64_t src = (idz ? __ldg(idz + i) * stride_z : 0) + __ldg(idx + j);
+    out[e] = __ldg(data + src * width + c);
+  }
+}
+
 // torch.optim.Adam (training.py:17,146), defaults: no weight decay, no amsgrad
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,

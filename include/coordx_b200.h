@@ -172,6 +172,14 @@ int coordx_optim_step(int n_tensors, float* const* params, const float* const* g
                       float* const* exp_avg_sq, const int64_t* numel, float* state, float beta1, float beta2,
                       float eps, float max_grad_norm, float lr_gamma, void* stream);
 
+/* ---- batch producer of the video / volume path: dataio.py:575-600 (Implicit3DWrapper.__getitem__) gathers the
+ * ground truth of a training batch, data[coord_idx[:, None] * n_xy + coord_idy[None, :], :], on the CPU and copies it
+ * to the GPU every iteration; here `data` [rows, width] is device-resident.
+ * out[(i * m + j), :] = data[idz[i] * stride_z + idx[j], :]   (idz == NULL: one level, nz ignored).
+ * idz [nz], idx [m]: int64 device arrays; the caller guarantees they are in range.                                    */
+int coordx_gather_rows(const float* data, int width, const int64_t* idz, int64_t nz, int64_t stride_z,
+                       const int64_t* idx, int64_t m, float* out, void* stream);
+
 /* ---- feature-interpolated points: the gather + lerp + fusion of ray_rendering.py:133-145 (get_pts_pred, split=True)
  * idx [n_points, n_axes] fractional indices into feats[c] [n[c], feat_width]  ->  h [n_points, feat_width], the
  * fused per-point features; they go through the trunk as a 1 x n_points grid (coordx_trunk_forward with a first
