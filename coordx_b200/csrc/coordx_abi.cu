@@ -41,17 +41,6 @@ static int mlp_forward(const Layer* L, int nl, const float* X, int64_t ldx, int 
   return 0;
 }
 
-// Wt[c, r] = W[r, c]
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wt) {
-  __shared__ float t[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int i = ty; i < 32; i += 8)
-    if (r0 + i < rows && c0 + tx < cols) t[i][tx] = W[(size_t)(r0 + i) * cols + c0 + tx];
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8)
-    if (c0 + i < cols && r0 + tx < rows) Wt[(size_t)(c0 + i) * rows + r0 + tx] = t[tx][i];
-}
-
 // dX[M,K] = dZ[M,N] W[N,K] (* act'(Zprev)) on the tensor cores (3xTF32) when the shape pays: W is transposed into `wt`
 // first so that both operands are K-major.  Returns 1 when it launched, 0 when the caller should take the FFMA kernel.
 static int dx_tensor(const float* dZ, int64_t lddz, const float* W, int M, int N, int K, float* dX, int64_t lddx,
@@ -103,7 +92,7 @@ static int get_fork(int slot, Fork** out) {
 // M * max width floats.  dX (nullable) [M, L[0].in].  fork (nullable): run dW / db on its side stream.
 static int mlp_backward(const Layer* L, int nl, const float* X, int64_t ldx, int M, float* const* Zs, float* const* As,
                         const float* dY, float* d0, float* d1, float* dX, float S, cudaStream_t st, Fork* fork = nullptr,
-                        float* wt = nullptr) {
+                        float* wt = nullptr, float* tw = nullptr, size_t tw_floats = 0) {
   const float* dz = dY;
   float* bufs[2] = {d0, d1};
   int which = 0;
@@ -124,7 +113,11 @@ static int mlp_backward(const Layer* L, int nl, const float* X, int64_t ldx, int
       CX_CUDA(cudaStreamWaitEvent(fork->side, fork->ev_main[l], 0));
       gs = fork->side;
     }
-    if (L[l].dW) CX_TRY(linear_backward_dw(dz, L[l].out, in, ldin, M, L[l].out, L[l].in, L[l].dW, gs));
+    if (L[l].dW) {
+      int on_tc = 0;
+      CX_TRY(dw_tensor(dz, L[l].out, in, ldin, M, L[l].out, L[l].in, L[l].dW, tw, tw_floats, gs, &on_tc));
+      if (!on_tc) CX_TRY(linear_backward_dw(dz, L[l].out, in, ldin, M, L[l].out, L[l].in, L[l].dW, gs));
+    }
     if (L[l].db) CX_TRY(bias_backward(dz, L[l].out, M, L[l].out, L[l].bscale, L[l].db, gs));
     // the dX below overwrites the buffer that held dz_{l+1}: the side stream must be done reading it
     if (side_pending >= 0) {
@@ -195,6 +188,8 @@ struct ChainWs {
   float* tmp0;
   float* tmp1;
   float* wt;        // backward: one transposed weight matrix (the dX GEMM as X . W^T^T on the tensor cores)
+  float* tw;        // backward: transposed dZ / input chunks of the weight-gradient GEMM (dw_tensor)
+  size_t tw_floats;
 };
 
 static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backward, ChainWs& w) {
@@ -208,11 +203,15 @@ static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backw
     w.d0 = ar.get<float>((size_t)M * maxw);
     w.d1 = ar.get<float>((size_t)M * maxw);
     w.wt = ar.get<float>((size_t)maxw * maxw);
+    w.tw_floats = M >= 128 && maxw >= 64 ? (size_t)2 * maxw * ((min(M, (int64_t)DW_ROWS) + 31) / 32 * 32) : 0;
+    w.tw = w.tw_floats ? ar.get<float>(w.tw_floats) : nullptr;
     w.tmp0 = w.tmp1 = nullptr;
   } else {
     w.tmp0 = ar.get<float>((size_t)M * maxw);
     w.tmp1 = ar.get<float>((size_t)M * maxw);
     w.wt = nullptr;
+    w.tw = nullptr;
+    w.tw_floats = 0;
   }
 }
 
@@ -403,7 +402,7 @@ int coordx_branch_backward(const coordx_net* net, int branch, const float* coord
   CX_TRY(mlp_forward(L, nl, coords, net->branch_in[branch], (int)n, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
   Fork* fork = nullptr;
   CX_TRY(get_fork(branch, &fork));
-  return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords, S, st, fork, w.wt);
+  return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords, S, st, fork, w.wt, w.tw, w.tw_floats);
 }
 
 // Training-mode pair: the forward keeps every layer's pre-activation / activation in `save` (the backward
@@ -440,7 +439,7 @@ int coordx_branch_backward_saved(const coordx_net* net, int branch, const float*
   Fork* fork = nullptr;
   CX_TRY(get_fork(branch, &fork));
   return mlp_backward(L, nl, coords, net->branch_in[branch], (int)n, w.Z, w.A, dfeat, w.d0, w.d1, dcoords,
-                      30.f * net->act_scale, st, fork, w.wt);
+                      30.f * net->act_scale, st, fork, w.wt, w.tw, w.tw_floats);
 }
 
 // -------------------------------------------------------------------------- trunk
@@ -550,7 +549,7 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
       fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, H0);
       CX_LAUNCH_CHECK();
       CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
-      CX_TRY(mlp_backward(L, nl, H0, net->hidden, (int)pts, w.Z, w.A, dY, w.d0, w.d1, dH0, S, st, nullptr, w.wt));
+      CX_TRY(mlp_backward(L, nl, H0, net->hidden, (int)pts, w.Z, w.A, dY, w.d0, w.d1, dH0, S, st, nullptr, w.wt, w.tw, w.tw_floats));
       dh = dH0;
     }
     for (int b = 0; b < C; ++b) {

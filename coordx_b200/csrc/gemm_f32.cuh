@@ -315,6 +315,81 @@ static int linear_backward_dw(const float* dZ, int64_t lddz, const float* X, int
   return launch_sgemm<false, false, EPI_ATOMIC>(g, st);
 }
 
+// Wt[c, r] = W[r, c]
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wt) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < rows && c0 + tx < cols) t[i][tx] = W[(size_t)(r0 + i) * cols + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) Wt[(size_t)(c0 + i) * rows + r0 + tx] = t[tx][i];
+}
+
+// dst[c, m] = src[m, c] for m < rows, 0 for rows <= m < mpad   (dst [cols, mpad]): operands of the TN weight-gradient GEMM
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int mpad,
+                                                            float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) t[i][tx] = (r0 + i < rows && c0 + tx < cols) ? src[(size_t)(r0 + i) * ld + c0 + tx] : 0.f;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < mpad) dst[(size_t)(c0 + i) * mpad + r0 + tx] = t[tx][i];
+}
+
+// dW[N,K] += dZ[M,N]^T X[M,K] on the tensor cores (3xTF32): the contraction runs over the ROWS, so both operands are
+// transposed into `tw` first ([N, Mpad] and [K, Mpad], rows padded with zeros to a multiple of 32, DW_ROWS rows at a
+// time) and the NT kernel runs with its K range split over the CTAs, adding into dW with atomics.  The FFMA split-K
+// kernel it replaces took 25-48 us per 2048 x 256 x 256 layer and 140 us per 1992 x 1024 x 1024 layer of the video net
+// - and competed for SMs with the latency-bound dX chain.  Returns 1 in *launched when it ran.
+constexpr int DW_ROWS = 4096;
+static int dw_tensor(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int M, int N, int K, float* dW, float* tw,
+                     size_t tw_floats, cudaStream_t st, int* launched) {
+  *launched = 0;
+  const char* e = getenv("COORDX_FP32_GEMM");
+  if (!tw || (e && strcmp(e, "ffma") == 0) || N < 64 || K < 64 || M < 128) return 0;
+  const int rows_max = min(M, DW_ROWS), pad_max = (rows_max + 31) / 32 * 32;
+  if (tw_floats < (size_t)(N + K) * pad_max) return 0;
+  float* tz = tw;
+  float* tx = tw + (size_t)N * pad_max;
+  for (int m0 = 0; m0 < M; m0 += DW_ROWS) {
+    const int rows = min(DW_ROWS, M - m0), mpad = (rows + 31) / 32 * 32;
+    transpose_pad_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)(mpad / 32)), 256, 0, st>>>(dZ + (size_t)m0 * lddz, lddz, rows, N, mpad, tz);
+    CX_LAUNCH_CHECK();
+    transpose_pad_kernel<<<dim3((unsigned)cdiv(K, 32), (unsigned)(mpad / 32)), 256, 0, st>>>(X + (size_t)m0 * ldx, ldx, rows, K, mpad, tx);
+    CX_LAUNCH_CHECK();
+    g3::Args t{};
+    t.A = tz; t.lda = mpad; t.B = tx; t.ldb = mpad; t.M = N; t.N = K; t.K = mpad;
+    t.Y = dW; t.ldc = K; t.cs = 1; t.act = -1; t.atomic = 1;
+    const bool wide = K >= 256 && cdiv(N, 128) * cdiv(K, 256) >= 32;
+    const int64_t tiles = cdiv(N, 128) * cdiv(K, wide ? 256 : 64);
+    const int nk = mpad / 32;
+    int splits = (int)max((int64_t)1, min((int64_t)nk, cdiv(148, tiles)));
+    const int per = (nk + splits - 1) / splits;
+    t.ksplits = (nk + per - 1) / per;                  // every split non-empty
+    CX_TRY(wide ? g3::launch_bn<256>(t, st) : g3::launch_bn<64>(t, st));
+  }
+  *launched = 1;
+  return 0;
+}
+
+// Y[M,N] += A[M,K] W[K,N] on the tensor cores (3xTF32, atomic epilogue): W is given TRANSPOSED (`wt` [N,K], made once by
+// the caller with transpose_kernel), so this is the NT kernel.  Returns 1 in *launched when the shape pays.
+static int nn_tensor_acc(const float* A, int64_t lda, const float* wt, int M, int N, int K, float* Y, int64_t ldy, cudaStream_t st,
+                         int* launched) {
+  *launched = 0;
+  const char* e = getenv("COORDX_FP32_GEMM");
+  if (!wt || (e && strcmp(e, "ffma") == 0) || M < 96 || N < 64 || K < 128 || K % 32 != 0 || (lda & 3)) return 0;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(wt)) & 15) return 0;
+  g3::Args t{};
+  t.A = A; t.lda = lda; t.B = wt; t.ldb = K; t.M = M; t.N = N; t.K = K;
+  t.Y = Y; t.ldc = ldy; t.cs = 1; t.act = -1; t.atomic = 1; t.ksplits = 1;
+  const bool wide = N >= 256 && cdiv(M, 128) * cdiv(N, 256) >= 32;
+  CX_TRY(wide ? g3::launch_bn<256>(t, st) : g3::launch_bn<64>(t, st));
+  *launched = 1;
+  return 0;
+}
+
 // db[n] += scale * sum_m dZ[m,n]
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ dZ, int64_t ld, int M, int N, float scale, float* __restrict__ db, int rows_per_block) {

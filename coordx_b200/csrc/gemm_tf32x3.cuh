@@ -53,6 +53,10 @@ struct Args {
   float S;
   const float* zprev;  // dX form (nullable): the result is multiplied by act'(zprev[m * ldz + n]) and stored to Y
   int64_t ldz;
+  // weight-gradient form (dw_tensor): the K range is split over gridDim.z CTAs (`ksplits`, every split non-empty) and
+  // the plain product is ADDED to Y with atomics (no bias, activation or Z output)
+  int ksplits;
+  int atomic;
 };
 
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -99,7 +103,12 @@ gemm_tf32x3_kernel(const Args g) {
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + SM_BAR + 40);
   constexpr int W_MMA = 8;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nk = g.K / BK;
+  int nk = g.K / BK, kc0 = 0;                      // this CTA's K chunks: [kc0, kc0 + nk)
+  if (g.ksplits > 1) {
+    const int per = (nk + g.ksplits - 1) / g.ksplits;
+    kc0 = (int)blockIdx.z * per;
+    nk = min(per, nk - kc0);
+  }
 
   if (warp == W_MMA) {
     if (lane == 0) {
@@ -149,7 +158,7 @@ gemm_tf32x3_kernel(const Args g) {
     // memory and are not needed before chunk kc + 1 has been written too - a whole chunk period to cover the L2 latency
     float4 ra[2][4], rb[2][BN / 32];
     auto gload = [&](int set, int kc) {
-      const int k0 = kc * BK + piece * 4;
+      const int k0 = (kc0 + kc) * BK + piece * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m0 + rbase + 32 * i;
@@ -208,6 +217,12 @@ gemm_tf32x3_kernel(const Args g) {
       if (m < g.M && nb < g.N) {
         const bool full = nb + 8 <= g.N;
         float v[8];
+        if (g.atomic) {                                 // split-K weight gradient: Y += partial product
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (nb + i < g.N) atomicAdd(&g.Y[(int64_t)m * g.ldc + (int64_t)(nb + i) * g.cs], __uint_as_float(r[i]) + __uint_as_float(r2[i]));
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           v[i] = (__uint_as_float(r[i]) + __uint_as_float(r2[i])) + add1 + ((g.bias && nb + i < g.N) ? __ldg(g.bias + nb + i) * g.bscale : 0.f);
@@ -274,7 +289,7 @@ static int tile_n(const Args& a) {
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return 0;
   const int64_t work = (int64_t)a.M * a.N * a.K;
   if (a.N >= 128 && cdiv(a.M, BM) * cdiv(a.N, 256) >= 32 && work >= ((int64_t)1 << 28)) return 256;
-  if (a.M >= 256 && a.K >= 128 && work >= ((int64_t)1 << 24)) return 64;
+  if (a.M >= 96 && a.K >= 128 && work >= ((int64_t)1 << 24)) return 64;
   return 0;
 }
 static bool usable(const Args& a) { return tile_n(a) != 0; }
@@ -283,7 +298,7 @@ template <int BN>
 static int launch_bn(const Args& a, cudaStream_t st) {
   static AttrOnce once;
   CX_TRY(once.set(gemm_tf32x3_kernel<BN>, (int)Cfg<BN>::SM_TOTAL));
-  dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, BM));
+  dim3 grid((unsigned)cdiv(a.N, BN), (unsigned)cdiv(a.M, BM), (unsigned)max(a.ksplits, 1));
   gemm_tf32x3_kernel<BN><<<grid, THREADS, Cfg<BN>::SM_TOTAL, st>>>(a);
   CX_LAUNCH_CHECK();
   return 0;

@@ -126,7 +126,17 @@ combine_kernel(const float* __restrict__ T, float* __restrict__ G, const float* 
 struct Bufs {
   float *U, *TU, *Fin, *V, *TV;                        // forward
   float *TUr, *TVr, *G, *Hm, *RA, *RB, *dFin;          // backward
+  float *wt, *tw;                                      // backward: W_h transposed; operand chunks of the tensor-core weight gradient
+  size_t tw_floats;
+  float *Do, *DoT, *TVrT, *TUrT;                       // backward, tensor-core reductions of dout: one channel of dout [R, Jpad], its
+  int64_t Jpad, Rpad;                                  // transpose [J, Rpad], and the transposed [cos | sin] tables [2Nh, Jpad], [2Nh, Rpad]
 };
+
+// the two reductions of dout over the grid run on the tensor cores when the tables are small enough to transpose
+static bool reductions_on_tc(const Plan& p) {
+  const int64_t jp = (p.inner + 31) / 32 * 32, rp = (p.R + 31) / 32 * 32;
+  return p.R >= 96 && p.inner >= 128 && p.Nh >= 64 && (int64_t)2 * p.Nh * (jp + rp) + p.R * jp + p.inner * rp <= ((int64_t)96 << 20);
+}
 
 static void carve(Arena& ar, const Plan& p, bool backward, Bufs& b) {
   b = Bufs{};
@@ -147,6 +157,18 @@ static void carve(Arena& ar, const Plan& p, bool backward, Bufs& b) {
     b.TVr = ar.get<float>((size_t)p.inner * 2 * p.Nh);
     b.Hm = ar.get<float>((size_t)p.O * p.inner * 2 * p.Nh);
     b.RB = ar.get<float>((size_t)p.inner * p.Nh);
+    b.wt = ar.get<float>((size_t)p.Nh * p.Kin);
+    const int64_t rows = min(max(p.R, p.inner), (int64_t)DW_ROWS);
+    b.tw_floats = (size_t)(p.Nh + p.Kin) * (size_t)((rows + 31) / 32 * 32);
+    b.tw = ar.get<float>(b.tw_floats);
+    if (reductions_on_tc(p)) {
+      b.Jpad = (p.inner + 31) / 32 * 32;
+      b.Rpad = (p.R + 31) / 32 * 32;
+      b.Do = ar.get<float>((size_t)p.R * b.Jpad);
+      b.DoT = ar.get<float>((size_t)p.inner * b.Rpad);
+      b.TVrT = ar.get<float>((size_t)2 * p.Nh * b.Jpad);
+      b.TUrT = ar.get<float>((size_t)2 * p.Nh * b.Rpad);
+    }
   }
 }
 
@@ -232,6 +254,16 @@ static bool backward_fits(const coordx_net* net, const int64_t* n, int64_t r0, i
   return words * 4.0 < 16e9 && p.R < (1 << 30) && p.inner < (1 << 30);
 }
 
+// dst[r, j] = src[(r * J + j) * stride] for j < J, 0 for J <= j < jpad   (one channel of the interleaved dout, rows padded)
+__global__ void __launch_bounds__(256)
+channel_pad_kernel(const float* __restrict__ src, int stride, int R, int J, int jpad, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int64_t)R * jpad) return;
+  const int64_t r = i / jpad;
+  const int j = (int)(i - r * jpad);
+  dst[i] = j < J ? __ldg(src + (r * J + j) * stride) : 0.f;
+}
+
 static int backward(const coordx_net* net, const float* const* feats, const int64_t* n, int64_t r0, int64_t r1,
                     const float* dout, coordx_grads* grads, float* const* dfeat, void* ws, size_t ws_bytes, cudaStream_t st) {
   const Plan p = make_plan(net, n, r0, r1);
@@ -253,7 +285,31 @@ static int backward(const coordx_net* net, const float* const* feats, const int6
   table_cs_kernel<<<(unsigned)cdiv((int64_t)J * Nh, 256), 256, 0, st>>>(b.V, S, J, Nh, N2, b.TVr);
   CX_LAUNCH_CHECK();
   // the two reductions of dout over the grid
-  for (int o = 0; o < p.O; ++o) {
+  const char* ffma_env = getenv("COORDX_FP32_GEMM");
+  const bool red_tc = b.Do != nullptr && !(ffma_env && strcmp(ffma_env, "ffma") == 0);
+  if (red_tc) {
+    // tensor cores (3xTF32): G_o = D_o TVr and H_o = D_o^T TUr as NT GEMMs over zero-padded, transposed operands
+    const int jp = (int)b.Jpad, rp = (int)b.Rpad;
+    transpose_pad_kernel<<<dim3((unsigned)cdiv(N2, 32), (unsigned)(jp / 32)), 256, 0, st>>>(b.TVr, N2, J, N2, jp, b.TVrT);
+    CX_LAUNCH_CHECK();
+    transpose_pad_kernel<<<dim3((unsigned)cdiv(N2, 32), (unsigned)(rp / 32)), 256, 0, st>>>(b.TUr, N2, R, N2, rp, b.TUrT);
+    CX_LAUNCH_CHECK();
+    for (int o = 0; o < p.O; ++o) {
+      channel_pad_kernel<<<(unsigned)cdiv((int64_t)R * jp, 256), 256, 0, st>>>(dout + o, p.O, R, J, jp, b.Do);
+      CX_LAUNCH_CHECK();
+      transpose_pad_kernel<<<dim3((unsigned)cdiv(J, 32), (unsigned)(rp / 32)), 256, 0, st>>>(b.Do, jp, R, J, rp, b.DoT);
+      CX_LAUNCH_CHECK();
+      g3::Args t{};
+      t.A = b.Do; t.lda = jp; t.B = b.TVrT; t.ldb = jp; t.M = R; t.N = N2; t.K = jp;
+      t.Y = b.G + (int64_t)o * R * N2; t.ldc = N2; t.cs = 1; t.act = -1;
+      CX_TRY((N2 >= 256 && cdiv(R, 128) * cdiv(N2, 256) >= 32) ? g3::launch_bn<256>(t, st) : g3::launch_bn<64>(t, st));
+      g3::Args u{};
+      u.A = b.DoT; u.lda = rp; u.B = b.TUrT; u.ldb = rp; u.M = J; u.N = N2; u.K = rp;
+      u.Y = b.Hm + (int64_t)o * J * N2; u.ldc = N2; u.cs = 1; u.act = -1;
+      CX_TRY((N2 >= 256 && cdiv(J, 128) * cdiv(N2, 256) >= 32) ? g3::launch_bn<256>(u, st) : g3::launch_bn<64>(u, st));
+    }
+  }
+  for (int o = 0; o < (red_tc ? 0 : p.O); ++o) {
     GemmArgs g{};                                   // G_o [R, 2Nh] = D_o [R, J] . TVr [J, 2Nh]
     g.A = dout + o; g.lda = p.inner * p.O; g.sa = p.O;
     g.B = b.TVr; g.ldb = N2;
@@ -277,23 +333,41 @@ static int backward(const coordx_net* net, const float* const* feats, const int6
   if (grads->layer_b[Lf]) CX_TRY(bias_backward(dout, p.O, (int)min(p.R * p.inner, (int64_t)INT32_MAX), p.O, 1.f, grads->layer_b[Lf], st));
   // hidden trunk layer
   if (grads->layer_b[Lh]) CX_TRY(bias_backward(b.RA, Nh, R, Nh, 1.f, grads->layer_b[Lh], st));
+  // (weight gradients and feature gradients on the tensor cores where the shape pays - 3xTF32 with an atomic epilogue,
+  //  dw_tensor / nn_tensor_acc in gemm_f32.cuh - else the FFMA kernels)
   if (grads->layer_w[Lh]) {
-    CX_TRY(linear_backward_dw(b.RA, Nh, f0, p.Kin, R, Nh, p.Kin, grads->layer_w[Lh], st));
-    CX_TRY(linear_backward_dw(b.RB, Nh, fin, p.Kin, J, Nh, p.Kin, grads->layer_w[Lh], st));
+    int tc = 0;
+    CX_TRY(dw_tensor(b.RA, Nh, f0, p.Kin, R, Nh, p.Kin, grads->layer_w[Lh], b.tw, b.tw_floats, st, &tc));
+    if (!tc) CX_TRY(linear_backward_dw(b.RA, Nh, f0, p.Kin, R, Nh, p.Kin, grads->layer_w[Lh], st));
+    CX_TRY(dw_tensor(b.RB, Nh, fin, p.Kin, J, Nh, p.Kin, grads->layer_w[Lh], b.tw, b.tw_floats, st, &tc));
+    if (!tc) CX_TRY(linear_backward_dw(b.RB, Nh, fin, p.Kin, J, Nh, p.Kin, grads->layer_w[Lh], st));
   }
   // branch features: dA += RA W, dB += RB W
+  if (dfeat[0] || (p.C == 2 && dfeat[1])) {
+    dim3 tg((unsigned)cdiv(p.Kin, 32), (unsigned)cdiv(Nh, 32));
+    transpose_kernel<<<tg, 256, 0, st>>>(net->layer_w[Lh], Nh, p.Kin, b.wt);      // W_h [Nh, Kin] -> [Kin, Nh]
+    CX_LAUNCH_CHECK();
+  }
   if (dfeat[0]) {
-    GemmArgs g{};
-    g.A = b.RA; g.lda = Nh; g.B = net->layer_w[Lh]; g.ldb = p.Kin; g.M = R; g.N = p.Kin; g.K = Nh;
-    g.Y = dfeat[0] + r0 * p.Kin; g.ldc = p.Kin;
-    CX_TRY((launch_sgemm<true, false, EPI_ATOMIC>(g, st)));
+    int tc = 0;
+    CX_TRY(nn_tensor_acc(b.RA, Nh, b.wt, R, p.Kin, Nh, dfeat[0] + r0 * p.Kin, p.Kin, st, &tc));
+    if (!tc) {
+      GemmArgs g{};
+      g.A = b.RA; g.lda = Nh; g.B = net->layer_w[Lh]; g.ldb = p.Kin; g.M = R; g.N = p.Kin; g.K = Nh;
+      g.Y = dfeat[0] + r0 * p.Kin; g.ldc = p.Kin;
+      CX_TRY((launch_sgemm<true, false, EPI_ATOMIC>(g, st)));
+    }
   }
   if (p.C == 2) {
     if (dfeat[1]) {
-      GemmArgs g{};
-      g.A = b.RB; g.lda = Nh; g.B = net->layer_w[Lh]; g.ldb = p.Kin; g.M = J; g.N = p.Kin; g.K = Nh;
-      g.Y = dfeat[1]; g.ldc = p.Kin;
-      CX_TRY((launch_sgemm<true, false, EPI_ATOMIC>(g, st)));
+      int tc = 0;
+      CX_TRY(nn_tensor_acc(b.RB, Nh, b.wt, J, p.Kin, Nh, dfeat[1], p.Kin, st, &tc));
+      if (!tc) {
+        GemmArgs g{};
+        g.A = b.RB; g.lda = Nh; g.B = net->layer_w[Lh]; g.ldb = p.Kin; g.M = J; g.N = p.Kin; g.K = Nh;
+        g.Y = dfeat[1]; g.ldc = p.Kin;
+        CX_TRY((launch_sgemm<true, false, EPI_ATOMIC>(g, st)));
+      }
     }
   } else {
     CX_TRY(linear_backward_dx(b.RB, Nh, net->layer_w[Lh], J, Nh, p.Kin, b.dFin, p.Kin, nullptr, 0, -1, S, st));
