@@ -139,7 +139,9 @@ static int mlp_backward(const Layer* L, int nl, const float* X, int64_t ldx, int
       dz = bufs[which];
       which ^= 1;
     } else if (dX) {
-      CX_TRY(linear_backward_dx(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, dX, L[l].in, nullptr, 0, -1, S, st));
+      int on_tc = 0;                                // (the input gradient of the chain: the fused features of the fp32 trunk)
+      CX_TRY(dx_tensor(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, dX, L[l].in, nullptr, 0, -1, S, wt, st, &on_tc));
+      if (!on_tc) CX_TRY(linear_backward_dx(dz, L[l].out, L[l].W, M, L[l].out, L[l].in, dX, L[l].in, nullptr, 0, -1, S, st));
     }
   }
   if (side_pending >= 0) CX_CUDA(cudaStreamWaitEvent(st, fork->ev_side[side_pending], 0));     // join
@@ -203,7 +205,7 @@ static void carve_chain(Arena& ar, const Layer* L, int nl, int64_t M, bool backw
     w.d0 = ar.get<float>((size_t)M * maxw);
     w.d1 = ar.get<float>((size_t)M * maxw);
     w.wt = ar.get<float>((size_t)maxw * maxw);
-    w.tw_floats = M >= 128 && maxw >= 64 ? (size_t)2 * maxw * ((min(M, (int64_t)DW_ROWS) + 31) / 32 * 32) : 0;
+    w.tw_floats = M >= 128 && maxw >= 64 ? (size_t)2 * maxw * ((min(M, (int64_t)dw_rows(2 * maxw)) + 31) / 32 * 32) : 0;
     w.tw = w.tw_floats ? ar.get<float>(w.tw_floats) : nullptr;
     w.tmp0 = w.tmp1 = nullptr;
   } else {
@@ -497,7 +499,10 @@ int coordx_trunk_forward(const coordx_net* net, const float* const* feats, const
     const int64_t pts = ch.pts;
     float* o = out + ch.first_pt * ow;
     float* h0 = nl > 0 ? H0 : o;            // approx_layers == num_hidden_layers+1: the fused value is the output
-    fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, h0);
+    if (fuse_fwd_vec4_ok(fa, h0))
+      fuse_fwd_vec4_kernel<<<(unsigned)cdiv(pts * (net->hidden / 4), 256), 256, 0, st>>>(fa, pts, h0);
+    else
+      fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, h0);
     CX_LAUNCH_CHECK();
     if (nl > 0) CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, o, nullptr, nullptr, w.tmp0, w.tmp1, S, st));
     return 0;
@@ -546,7 +551,10 @@ int coordx_trunk_backward(const coordx_net* net, const float* const* feats, cons
     const float* dY = dout + ch.first_pt * ow;
     const float* dh = dY;
     if (nl > 0) {
-      fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, H0);
+      if (fuse_fwd_vec4_ok(fa, H0))
+        fuse_fwd_vec4_kernel<<<(unsigned)cdiv(pts * (net->hidden / 4), 256), 256, 0, st>>>(fa, pts, H0);
+      else
+        fuse_fwd_kernel<<<(unsigned)cdiv(pts * net->hidden, 256), 256, 0, st>>>(fa, pts, H0);
       CX_LAUNCH_CHECK();
       CX_TRY(mlp_forward(L, nl, H0, net->hidden, (int)pts, nullptr, w.Z, w.A, nullptr, nullptr, S, st));
       CX_TRY(mlp_backward(L, nl, H0, net->hidden, (int)pts, w.Z, w.A, dY, w.d0, w.d1, dH0, S, st, nullptr, w.wt, w.tw, w.tw_floats));

@@ -342,18 +342,27 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restr
 // time) and the NT kernel runs with its K range split over the CTAs, adding into dW with atomics.  The FFMA split-K
 // kernel it replaces took 25-48 us per 2048 x 256 x 256 layer and 140 us per 1992 x 1024 x 1024 layer of the video net
 // - and competed for SMs with the latency-bound dX chain.  Returns 1 in *launched when it ran.
-constexpr int DW_ROWS = 4096;
+// rows per pass: as many as a 64 MB scratch area holds for the two transposed operands ([N + K, rows] fp32), between 4096
+// and 32768 - the fp32 trunk feeds 32768-point chunks, and eight 4096-row passes per chunk were launch-latency-bound
+constexpr int DW_ROWS = 4096;                      // (the separable path sizes its scratch with this minimum)
+static int dw_rows(int n_plus_k) {
+  const int64_t r = ((int64_t)16 << 20) / max(n_plus_k, 1);
+  return (int)min((int64_t)32768, max((int64_t)DW_ROWS, r / 32 * 32));
+}
 static int dw_tensor(const float* dZ, int64_t lddz, const float* X, int64_t ldx, int M, int N, int K, float* dW, float* tw,
                      size_t tw_floats, cudaStream_t st, int* launched) {
   *launched = 0;
   const char* e = getenv("COORDX_FP32_GEMM");
   if (!tw || (e && strcmp(e, "ffma") == 0) || N < 64 || K < 64 || M < 128) return 0;
-  const int rows_max = min(M, DW_ROWS), pad_max = (rows_max + 31) / 32 * 32;
+  // the largest pass the caller's scratch area allows (it was sized with dw_rows(2 * max width) or DW_ROWS)
+  int pass = dw_rows(N + K);
+  while (pass > DW_ROWS && tw_floats < (size_t)(N + K) * ((min(M, pass) + 31) / 32 * 32)) pass /= 2;
+  const int rows_max = min(M, pass), pad_max = (rows_max + 31) / 32 * 32;
   if (tw_floats < (size_t)(N + K) * pad_max) return 0;
   float* tz = tw;
   float* tx = tw + (size_t)N * pad_max;
-  for (int m0 = 0; m0 < M; m0 += DW_ROWS) {
-    const int rows = min(DW_ROWS, M - m0), mpad = (rows + 31) / 32 * 32;
+  for (int m0 = 0; m0 < M; m0 += pass) {
+    const int rows = min(pass, M - m0), mpad = (rows + 31) / 32 * 32;
     transpose_pad_kernel<<<dim3((unsigned)cdiv(N, 32), (unsigned)(mpad / 32)), 256, 0, st>>>(dZ + (size_t)m0 * lddz, lddz, rows, N, mpad, tz);
     CX_LAUNCH_CHECK();
     transpose_pad_kernel<<<dim3((unsigned)cdiv(K, 32), (unsigned)(mpad / 32)), 256, 0, st>>>(X + (size_t)m0 * ldx, ldx, rows, K, mpad, tx);
