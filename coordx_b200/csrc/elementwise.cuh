@@ -89,6 +89,20 @@ fuse_bwd_kernel(FuseArgs a, int b, const float* __restrict__ dH0, float* __restr
   const float fb = a.feat[b][ib * a.F + jj];
   const float cd = a.code ? a.code[jj] : 1.f;
   float acc = 0.f, acc_code = 0.f;
+  if (a.C == 2 && a.gs == 1 && !a.fba && !a.code && !dcode) {
+    // plain two-axis case: no index decode (the general loop below spends its time on 64-bit divisions: 0.6 TB/s)
+    //   b = 0: points (ib, t), t = index on axis 1;   b = 1: points (t, ib), t = row of the chunk
+    const float* dh = b == 0 ? dH0 + (ib_local * a.inner + t0) * a.Hd + jj : dH0 + (t0 * a.inner + ib_local) * a.Hd + jj;
+    const int64_t dstep = b == 0 ? a.Hd : a.inner * a.Hd;
+    const float* ot = b == 0 ? a.feat[1] + t0 * a.F + jj : a.feat[0] + (a.row0 + t0) * a.F + jj;
+    if (a.op == COORDX_FUSE_PROD) {
+      for (int64_t t = t0; t < t1; ++t, dh += dstep, ot += a.F) acc = fmaf(__ldg(dh), __ldg(ot), acc);
+    } else {
+      for (int64_t t = t0; t < t1; ++t, dh += dstep) acc += __ldg(dh);
+    }
+    atomicAdd(&dfeat[ib * a.F + jj], acc);
+    return;
+  }
   for (int64_t t = t0; t < t1; ++t) {
     // decode the other axes' indices from t (row-major over axes != b, axis 0 counts nrows)
     int64_t rem = t, q = 0, mul = 1;
