@@ -69,3 +69,21 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f), errors='replace').read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def test_forward_with_loss_validates_its_arguments_and_never_falls_back_to_a_cpu_path():
+    """host logic of SingleBVPNet.forward_with_loss (the loss fused into the trunk's last layer): an unknown loss is a
+    ValueError before anything is launched, CPU tensors raise like every other hot-path entry (no CPU fallback), and the
+    loss hook never stays set on the module."""
+    import pytest
+    import torch
+    from coordx_b200 import modules as M, _lib
+    m = M.SingleBVPNet(type='sine', out_features=1, hidden_features=64, split_mlp=True, fusion_operator='prod', quiet=True)
+    x = torch.linspace(-1, 1, 8).reshape(1, 8, 1, 1)
+    y = torch.linspace(-1, 1, 6).reshape(1, 1, 6, 1)
+    gt = torch.zeros(1, 48, 1)
+    with pytest.raises(ValueError):
+        m.forward_with_loss({'coords_split': [x, y]}, gt, 'huber')
+    with pytest.raises(_lib.CoordxError):
+        m.forward_with_loss({'coords_split': [x, y]}, gt, 'mse')
+    assert m.net.__dict__.get('_loss_hook') is None
